@@ -1,0 +1,125 @@
+"""CPU tests: the oracle is pinned to the reference before anything trusts it.
+
+1. against the committed golden vectors (tests/golden/ref_vectors.npz, produced by the
+   reference's own CpuBenchmark + DataGenerator, see tests/golden/make_golden.py);
+2. where oracle/_ref is present, against the reference library live on fresh inputs;
+3. the host-side generator mirror (vulkan_radix_sort_b200.datagen) against the reference's.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from vulkan_radix_sort_b200.datagen import DISTRIBUTIONS, DataGenerator, make_keys
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_vectors.npz")
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(GOLDEN)
+
+
+def _cases(golden):
+    return [tuple(int(x) for x in row) for row in golden["cases"]]
+
+
+def test_golden_fixture_present(golden):
+    assert len(_cases(golden)) >= 10
+
+
+def test_oracle_matches_golden_vectors(oracle, golden):
+    for seed, n, bits in _cases(golden):
+        tag = f"s{seed}_n{n}_b{bits}"
+        k, v = golden[tag + "_keys"], golden[tag + "_values"]
+        assert np.array_equal(oracle.sort_keys(k), golden[tag + "_sorted"]), tag
+        ok, ov = oracle.sort_key_value(k, v)
+        assert np.array_equal(ok, golden[tag + "_kv_keys"]), tag
+        assert np.array_equal(ov, golden[tag + "_kv_values"]), tag  # pins stability
+        pk, pv = oracle.sort_partitioned(k, v, n)
+        assert np.array_equal(pk, golden[tag + "_kv_keys"]), tag
+        assert np.array_equal(pv, golden[tag + "_kv_values"]), tag
+
+
+def test_oracle_sentinel_keys_keep_their_values(oracle, golden):
+    k, v = golden["sentinel_keys"], golden["sentinel_values"]
+    for fn in (oracle.sort_key_value, lambda a, b: oracle.sort_partitioned(a, b, a.size)):
+        ok, ov = fn(k, v)
+        assert np.array_equal(ok, golden["sentinel_kv_keys"])
+        assert np.array_equal(ov, golden["sentinel_kv_values"])
+
+
+def test_generator_mirror_matches_golden_inputs(golden):
+    for seed, n, bits in _cases(golden):
+        tag = f"s{seed}_n{n}_b{bits}"
+        k, v = DataGenerator(seed).generate(n, bits)
+        assert np.array_equal(k, golden[tag + "_keys"]), tag
+        assert np.array_equal(v, golden[tag + "_values"]), tag
+
+
+def test_generator_first_key_seed42():
+    # DataGenerator(42).Generate(n) starts with 1608637542 under libstdc++
+    assert int(DataGenerator(42).generate(4)[0][0]) == 1608637542
+
+
+def test_structural_restatement_equals_net_effect(oracle):
+    # partition boundaries of the reference (4096) and tail handling, all distributions
+    for dist in DISTRIBUTIONS:
+        for n in (1, 2, 4095, 4096, 4097, 12288, 12289, 30001):
+            k = make_keys(dist, n, seed=11)
+            v = np.arange(n, dtype=np.uint32)
+            a_k, a_v = oracle.sort_key_value(k, v)
+            b_k, b_v = oracle.sort_partitioned(k, v, n)
+            assert np.array_equal(a_k, b_k) and np.array_equal(a_v, b_v), (dist, n)
+            assert np.array_equal(a_k, np.sort(k, kind="stable"))
+            assert np.array_equal(a_v, np.argsort(k, kind="stable").astype(np.uint32))
+
+
+def test_indirect_contract_tail_untouched(oracle):
+    # count < max: only [0,count) is sorted, [count,max) keeps the caller's data
+    mx, count = 12288, 4113
+    k = make_keys("uniform", mx, seed=3)
+    v = make_keys("uniform", mx, seed=4)
+    ok, ov = oracle.sort_partitioned(k, v, count)
+    ek, ev = oracle.sort_key_value(k[:count], v[:count])
+    assert np.array_equal(ok[:count], ek) and np.array_equal(ov[:count], ev)
+    assert np.array_equal(ok[count:], k[count:]) and np.array_equal(ov[count:], v[count:])
+    ok2, _ = oracle.sort_partitioned(k, None, 0)
+    assert np.array_equal(ok2, k)
+
+
+def test_property_checkers(oracle):
+    k = make_keys("bits8", 50000, seed=5)
+    v = np.arange(k.size, dtype=np.uint32)
+    sk, sv = oracle.sort_key_value(k, v)
+    assert oracle.is_sorted(sk) and not oracle.is_sorted(k)
+    assert oracle.multiset_fingerprint(k, v) == oracle.multiset_fingerprint(sk, sv)
+    assert oracle.check_stable_permutation(k, sk, sv)
+    bad = sv.copy()
+    i = int(np.flatnonzero(sk[1:] == sk[:-1])[0])
+    bad[i], bad[i + 1] = bad[i + 1], bad[i]  # break stability only
+    assert not oracle.check_stable_permutation(k, sk, bad)
+    assert oracle.multiset_fingerprint(sk, bad) == oracle.multiset_fingerprint(sk, sv)  # same multiset
+    lost = sv.copy()
+    lost[7] = lost[8]  # a dropped / duplicated element changes the multiset
+    assert oracle.multiset_fingerprint(sk, lost) != oracle.multiset_fingerprint(sk, sv)
+
+
+def test_oracle_against_live_reference(oracle):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built on this machine")
+    for seed, n, bits in [(1, 1 << 18, 32), (2, 100003, 32), (3, 65537, 8), (4, 70000, 0)]:
+        k, v = oracle.ref_generate(seed, n, bits)
+        mk, mv = DataGenerator(seed).generate(n, bits)
+        assert np.array_equal(k, mk) and np.array_equal(v, mv)
+        rk, _ = oracle.ref_sort_keys(k)
+        assert np.array_equal(oracle.sort_keys(k), rk)
+        rkk, rkv, _ = oracle.ref_sort_key_value(k, v)
+        ok, ov = oracle.sort_key_value(k, v)
+        assert np.array_equal(ok, rkk) and np.array_equal(ov, rkv)
+    for dist in ("skewed", "all_ones", "sentinel_mix", "sorted", "reverse"):
+        k = make_keys(dist, 50001, seed=9)
+        v = np.arange(k.size, dtype=np.uint32)
+        rkk, rkv, _ = oracle.ref_sort_key_value(k, v)
+        ok, ov = oracle.sort_partitioned(k, v, k.size)
+        assert np.array_equal(ok, rkk) and np.array_equal(ov, rkv), dist

@@ -1,0 +1,454 @@
+// vrdx_api.cu — the vk_radix_sort C API on CUDA streams (host side of libvrdx_b200.so).
+//
+// Replaces the reference's host layer, src/vk_radix_sort.h.in:
+//   :141-277  vrdxCreateSorter / vrdxDestroySorter  (pipelines -> kernel attributes)
+//   :279-308  vrdxGetSorter[KeyValue]StorageRequirements
+//   :310-342  the four vrdxCmdSort* wrappers
+//   :344-507  gpuSort(): command recording  -> stream launches below (EnqueueSort)
+// "Recording" into a VkCommandBuffer becomes enqueueing on a cudaStream_t: asynchronous, no
+// host synchronisation, no host read of device memory, legal inside CUDA-graph capture.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#define VRDX_FORCE_VK_SHIM 1
+#include "vk_radix_sort.h"
+#include "vrdx_cuda.h"
+#include "vrdx_kernels.cuh"
+#include "vrdx_layout.h"
+
+using namespace vrdx;
+
+// ---------------------------------------------------------------------------- configuration
+// Tile shapes of the pass kernel (threads x keys per thread).  One CTA sorts one tile per pass.
+using KeysCfg = PassConfig<512, 16, false>;
+using PairCfg = PassConfig<512, 16, true>;
+constexpr uint32_t kMinTile = (KeysCfg::kTile < PairCfg::kTile) ? KeysCfg::kTile : PairCfg::kTile;
+
+struct VrdxSorter_T {
+  int device = 0;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  VrdxCudaAlgorithm algorithm = VRDX_CUDA_ALGORITHM_AUTO;
+  VrdxCudaTileLoad tile_load = VRDX_CUDA_TILE_LOAD_AUTO;
+  // The only mutable words: a sticky error and a launch counter (diagnostics, not sort state).
+  std::atomic<int> last_error{0};
+  std::atomic<uint32_t> last_launches{0};
+};
+
+struct VrdxQueryPool_T {
+  int device = 0;
+  std::vector<cudaEvent_t> events;
+  std::vector<uint8_t> recorded;
+};
+
+struct VrdxCudaImportedMemory_T {
+  int device = 0;
+  cudaExternalMemory_t ext = nullptr;
+  void* base = nullptr;
+  uint64_t size = 0;
+};
+
+namespace {
+
+int DeviceFromHandle(const void* h) { return (int)(reinterpret_cast<uintptr_t>(h)) - 1; }
+
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+void NoteError(VrdxSorter s, cudaError_t e) {
+  if (e != cudaSuccess) {
+    int expected = 0;
+    s->last_error.compare_exchange_strong(expected, (int)e);
+  }
+}
+
+VrdxQueryPool_T* Pool(VkQueryPool p) { return reinterpret_cast<VrdxQueryPool_T*>(p); }
+
+void Stamp(VrdxSorter s, cudaStream_t stream, VkQueryPool pool, uint32_t slot) {
+  if (!pool) return;
+  VrdxQueryPool_T* qp = Pool(pool);
+  if (slot >= qp->events.size()) {
+    NoteError(s, cudaErrorInvalidValue);
+    return;
+  }
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(stream, &cap);
+  cudaError_t e = (cap == cudaStreamCaptureStatusActive)
+                      ? cudaEventRecordWithFlags(qp->events[slot], stream, cudaEventRecordExternal)
+                      : cudaEventRecord(qp->events[slot], stream);
+  NoteError(s, e);
+  qp->recorded[slot] = 1;
+}
+
+template <typename Cfg, bool KV>
+cudaError_t PrepareKernel() {
+  return cudaFuncSetAttribute(OnesweepKernel<Cfg::kThreads, Cfg::kItems, KV>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
+}
+
+template <typename Cfg, bool KV>
+cudaError_t LaunchPass(cudaStream_t stream, uint32_t grid, const PassArgs& args) {
+  OnesweepKernel<Cfg::kThreads, Cfg::kItems, KV><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(args);
+  return cudaGetLastError();
+}
+
+// The body of every vrdxCmdSort* (reference: gpuSort, h.in:344-507).
+void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or_max,
+                 VkBuffer indirectBuffer, VkDeviceSize indirectOffset, VkBuffer keysBuffer,
+                 VkDeviceSize keysOffset, VkBuffer valuesBuffer, VkDeviceSize valuesOffset,
+                 VkBuffer storageBuffer, VkDeviceSize storageOffset, VkQueryPool queryPool,
+                 uint32_t query) {
+  if (!sorter) return;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(commandBuffer);
+  DeviceGuard guard(sorter->device);
+  uint32_t launches = 0;
+
+  auto addr = [](VkBuffer b, VkDeviceSize off) -> char* {
+    return b ? reinterpret_cast<char*>(b) + off : nullptr;
+  };
+  const uint32_t* indirect = reinterpret_cast<const uint32_t*>(addr(indirectBuffer, indirectOffset));
+  uint32_t* keys = reinterpret_cast<uint32_t*>(addr(keysBuffer, keysOffset));
+  uint32_t* values = reinterpret_cast<uint32_t*>(addr(valuesBuffer, valuesOffset));
+  char* storage = addr(storageBuffer, storageOffset);
+  const bool kv = values != nullptr;
+
+  Stamp(sorter, stream, queryPool, query + 0);
+  if (n_or_max == 0 || !keys || !storage) {
+    if (n_or_max != 0) NoteError(sorter, cudaErrorInvalidValue);
+    for (uint32_t i = 1; i < 15; ++i) Stamp(sorter, stream, queryPool, query + i);
+    sorter->last_launches.store(0);
+    return;
+  }
+  if ((uint64_t)n_or_max >= kMaxOnesweepCount) {
+    // 30-bit look-back cells; larger counts need the reduce-then-scan path (not built yet).
+    NoteError(sorter, cudaErrorNotSupported);
+    for (uint32_t i = 1; i < 15; ++i) Stamp(sorter, stream, queryPool, query + i);
+    sorter->last_launches.store(0);
+    return;
+  }
+
+  const StorageLayout lay = ComputeLayout(n_or_max, kMinTile);
+  StorageHeader* hdr = reinterpret_cast<StorageHeader*>(storage + lay.header_offset);
+  uint32_t* status[2] = {reinterpret_cast<uint32_t*>(storage + lay.status_a_offset),
+                         reinterpret_cast<uint32_t*>(storage + lay.status_b_offset)};
+  uint32_t* keys_alt = reinterpret_cast<uint32_t*>(storage + lay.keys_alt_offset);
+  uint32_t* vals_alt = reinterpret_cast<uint32_t*>(storage + lay.values_alt_offset);
+
+  const uint32_t tile = kv ? PairCfg::kTile : KeysCfg::kTile;
+  const uint32_t tiles = (uint32_t)CeilDiv(n_or_max, tile);
+
+  // Reset per-sort state inside the stream (reference: vkCmdFillBuffer of the global
+  // histogram, h.in:382): header (histograms, tickets) + the pass-0 look-back cells.
+  NoteError(sorter, cudaMemsetAsync(storage, 0,
+                                    lay.status_a_offset + (uint64_t)tiles * kRadix * sizeof(uint32_t),
+                                    stream));
+  ++launches;
+
+  {
+    uint64_t chunks = CeilDiv(n_or_max, (uint64_t)kHistChunk);
+    uint64_t cap = (uint64_t)sorter->sm_count * 4;
+    uint32_t grid = (uint32_t)(chunks < cap ? (chunks ? chunks : 1) : cap);
+    HistogramKernel<<<grid, kHistThreads, 0, stream>>>(keys, indirect, n_or_max, hdr);
+    NoteError(sorter, cudaGetLastError());
+    ++launches;
+  }
+  Stamp(sorter, stream, queryPool, query + 1);
+
+  for (uint32_t pass = 0; pass < (uint32_t)kPasses; ++pass) {
+    PassArgs args{};
+    args.indirect = indirect;
+    args.n_or_max = n_or_max;
+    args.pass = pass;
+    args.hdr = hdr;
+    args.status = status[pass & 1];
+    args.status_next = (pass + 1 < (uint32_t)kPasses) ? status[(pass + 1) & 1] : nullptr;
+    // ping-pong: user -> scratch on even passes, scratch -> user on odd ones (h.in:417-427)
+    args.keys_in = (pass & 1) ? keys_alt : keys;
+    args.keys_out = (pass & 1) ? keys : keys_alt;
+    args.vals_in = kv ? ((pass & 1) ? vals_alt : values) : nullptr;
+    args.vals_out = kv ? ((pass & 1) ? values : vals_alt) : nullptr;
+
+    // One fused kernel per pass: the reference's upsweep and spine slots collapse onto its start.
+    Stamp(sorter, stream, queryPool, query + 2 + 3 * pass + 0);
+    Stamp(sorter, stream, queryPool, query + 2 + 3 * pass + 1);
+    cudaError_t e = kv ? LaunchPass<PairCfg, true>(stream, tiles, args)
+                       : LaunchPass<KeysCfg, false>(stream, tiles, args);
+    NoteError(sorter, e);
+    ++launches;
+    Stamp(sorter, stream, queryPool, query + 2 + 3 * pass + 2);
+  }
+  Stamp(sorter, stream, queryPool, query + 14);
+  sorter->last_launches.store(launches);
+}
+
+}  // namespace
+
+// ============================================================================ C ABI
+
+extern "C" {
+
+VkResult vrdxCudaCreateSorter(const VrdxSorterCreateInfo* pCreateInfo,
+                              const VrdxCudaSorterOptions* pOptions, VrdxSorter* pSorter) {
+  if (!pCreateInfo || !pSorter) return VK_ERROR_INITIALIZATION_FAILED;
+  const int dev = DeviceFromHandle(pCreateInfo->device);
+  if (pCreateInfo->physicalDevice && DeviceFromHandle(pCreateInfo->physicalDevice) != dev)
+    return VK_ERROR_INITIALIZATION_FAILED;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) {
+    cudaGetLastError();
+    return VK_ERROR_INITIALIZATION_FAILED;
+  }
+  if (dev < 0 || dev >= count) return VK_ERROR_INITIALIZATION_FAILED;
+
+  cudaDeviceProp prop{};
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return VK_ERROR_INITIALIZATION_FAILED;
+  if (prop.major != 10) return VK_ERROR_FEATURE_NOT_PRESENT;  // kernels are built for sm_100a only
+
+  DeviceGuard guard(dev);
+  // "Pipeline creation": opt the pass kernels into their shared-memory footprint.
+  if (PrepareKernel<KeysCfg, false>() != cudaSuccess || PrepareKernel<PairCfg, true>() != cudaSuccess) {
+    cudaGetLastError();
+    return VK_ERROR_INITIALIZATION_FAILED;
+  }
+
+  VrdxSorter_T* s = new (std::nothrow) VrdxSorter_T();
+  if (!s) return VK_ERROR_OUT_OF_HOST_MEMORY;
+  s->device = dev;
+  s->sm_count = prop.multiProcessorCount;
+  s->cc_major = prop.major;
+  s->cc_minor = prop.minor;
+  if (pOptions && pOptions->structSize >= sizeof(VrdxCudaSorterOptions)) {
+    s->algorithm = pOptions->algorithm;
+    s->tile_load = pOptions->tileLoad;
+  }
+  *pSorter = s;
+  return VK_SUCCESS;
+}
+
+VkResult vrdxCreateSorter(const VrdxSorterCreateInfo* pCreateInfo, VrdxSorter* pSorter) {
+  return vrdxCudaCreateSorter(pCreateInfo, nullptr, pSorter);
+}
+
+void vrdxDestroySorter(VrdxSorter sorter) {
+  if (!sorter) return;
+  delete sorter;
+}
+
+void vrdxGetSorterStorageRequirements(VrdxSorter /*sorter*/, uint32_t maxElementCount,
+                                      VrdxSorterStorageRequirements* requirements) {
+  if (!requirements) return;
+  const StorageLayout lay = ComputeLayout(maxElementCount, kMinTile);
+  requirements->size = lay.total_keys;
+  requirements->usage = VK_BUFFER_USAGE_STORAGE_BUFFER_BIT | VK_BUFFER_USAGE_TRANSFER_DST_BIT;
+}
+
+void vrdxGetSorterKeyValueStorageRequirements(VrdxSorter /*sorter*/, uint32_t maxElementCount,
+                                              VrdxSorterStorageRequirements* requirements) {
+  if (!requirements) return;
+  const StorageLayout lay = ComputeLayout(maxElementCount, kMinTile);
+  requirements->size = lay.total_kv;
+  requirements->usage = VK_BUFFER_USAGE_STORAGE_BUFFER_BIT | VK_BUFFER_USAGE_TRANSFER_DST_BIT;
+}
+
+void vrdxCmdSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t elementCount,
+                 VkBuffer keysBuffer, VkDeviceSize keysOffset, VkBuffer storageBuffer,
+                 VkDeviceSize storageOffset, VkQueryPool queryPool, uint32_t query) {
+  EnqueueSort(commandBuffer, sorter, elementCount, nullptr, 0, keysBuffer, keysOffset, nullptr, 0,
+              storageBuffer, storageOffset, queryPool, query);
+}
+
+void vrdxCmdSortIndirect(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t maxElementCount,
+                         VkBuffer indirectBuffer, VkDeviceSize indirectOffset, VkBuffer keysBuffer,
+                         VkDeviceSize keysOffset, VkBuffer storageBuffer,
+                         VkDeviceSize storageOffset, VkQueryPool queryPool, uint32_t query) {
+  if (sorter && !indirectBuffer) {
+    NoteError(sorter, cudaErrorInvalidValue);
+    return;
+  }
+  EnqueueSort(commandBuffer, sorter, maxElementCount, indirectBuffer, indirectOffset, keysBuffer,
+              keysOffset, nullptr, 0, storageBuffer, storageOffset, queryPool, query);
+}
+
+void vrdxCmdSortKeyValue(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t elementCount,
+                         VkBuffer keysBuffer, VkDeviceSize keysOffset, VkBuffer valuesBuffer,
+                         VkDeviceSize valuesOffset, VkBuffer storageBuffer,
+                         VkDeviceSize storageOffset, VkQueryPool queryPool, uint32_t query) {
+  if (sorter && !valuesBuffer && elementCount) {
+    NoteError(sorter, cudaErrorInvalidValue);
+    return;
+  }
+  EnqueueSort(commandBuffer, sorter, elementCount, nullptr, 0, keysBuffer, keysOffset, valuesBuffer,
+              valuesOffset, storageBuffer, storageOffset, queryPool, query);
+}
+
+void vrdxCmdSortKeyValueIndirect(VkCommandBuffer commandBuffer, VrdxSorter sorter,
+                                 uint32_t maxElementCount, VkBuffer indirectBuffer,
+                                 VkDeviceSize indirectOffset, VkBuffer keysBuffer,
+                                 VkDeviceSize keysOffset, VkBuffer valuesBuffer,
+                                 VkDeviceSize valuesOffset, VkBuffer storageBuffer,
+                                 VkDeviceSize storageOffset, VkQueryPool queryPool, uint32_t query) {
+  if (sorter && (!indirectBuffer || (!valuesBuffer && maxElementCount))) {
+    NoteError(sorter, cudaErrorInvalidValue);
+    return;
+  }
+  EnqueueSort(commandBuffer, sorter, maxElementCount, indirectBuffer, indirectOffset, keysBuffer,
+              keysOffset, valuesBuffer, valuesOffset, storageBuffer, storageOffset, queryPool, query);
+}
+
+// ---------------------------------------------------------------------------- extensions
+
+int vrdxCudaGetLastError(VrdxSorter sorter) {
+  if (!sorter) return (int)cudaErrorInvalidResourceHandle;
+  return sorter->last_error.exchange(0);
+}
+
+const char* vrdxCudaGetErrorString(int error) { return cudaGetErrorString((cudaError_t)error); }
+
+uint32_t vrdxCudaGetLastLaunchCount(VrdxSorter sorter) {
+  return sorter ? sorter->last_launches.load() : 0u;
+}
+
+VkResult vrdxCudaCreateQueryPool(VkDevice device, uint32_t queryCount, VkQueryPool* pQueryPool) {
+  if (!pQueryPool || queryCount == 0) return VK_ERROR_INITIALIZATION_FAILED;
+  const int dev = DeviceFromHandle(device);
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || dev < 0 || dev >= count) {
+    cudaGetLastError();
+    return VK_ERROR_INITIALIZATION_FAILED;
+  }
+  DeviceGuard guard(dev);
+  VrdxQueryPool_T* qp = new (std::nothrow) VrdxQueryPool_T();
+  if (!qp) return VK_ERROR_OUT_OF_HOST_MEMORY;
+  qp->device = dev;
+  qp->events.resize(queryCount, nullptr);
+  qp->recorded.assign(queryCount, 0);
+  for (uint32_t i = 0; i < queryCount; ++i) {
+    if (cudaEventCreate(&qp->events[i]) != cudaSuccess) {
+      for (uint32_t j = 0; j < i; ++j) cudaEventDestroy(qp->events[j]);
+      delete qp;
+      cudaGetLastError();
+      return VK_ERROR_OUT_OF_DEVICE_MEMORY;
+    }
+  }
+  *pQueryPool = reinterpret_cast<VkQueryPool>(qp);
+  return VK_SUCCESS;
+}
+
+void vrdxCudaDestroyQueryPool(VkQueryPool queryPool) {
+  if (!queryPool) return;
+  VrdxQueryPool_T* qp = Pool(queryPool);
+  DeviceGuard guard(qp->device);
+  for (cudaEvent_t e : qp->events) cudaEventDestroy(e);
+  delete qp;
+}
+
+VkResult vrdxCudaGetQueryPoolResults(VkQueryPool queryPool, uint32_t firstQuery,
+                                     uint32_t queryCount, uint64_t* pNanoseconds) {
+  if (!queryPool || !pNanoseconds) return VK_ERROR_INITIALIZATION_FAILED;
+  VrdxQueryPool_T* qp = Pool(queryPool);
+  if ((uint64_t)firstQuery + queryCount > qp->events.size()) return VK_ERROR_INITIALIZATION_FAILED;
+  DeviceGuard guard(qp->device);
+  double t = 0.0;  // accumulate slot-to-slot so float milliseconds never lose resolution
+  for (uint32_t i = 0; i < queryCount; ++i) {
+    if (!qp->recorded[firstQuery + i]) return VK_NOT_READY;
+    if (i > 0) {
+      float ms = 0.f;
+      cudaError_t e = cudaEventElapsedTime(&ms, qp->events[firstQuery + i - 1], qp->events[firstQuery + i]);
+      if (e == cudaErrorNotReady) {
+        cudaGetLastError();
+        return VK_NOT_READY;
+      }
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        return VK_ERROR_UNKNOWN;
+      }
+      t += (double)ms * 1e6;
+    }
+    pNanoseconds[i] = (uint64_t)(t + 0.5);
+  }
+  return VK_SUCCESS;
+}
+
+VkResult vrdxCudaImportMemoryFd(VkDevice device, int fd, VkDeviceSize allocationSize, int dedicated,
+                                VrdxCudaImportedMemory* pMemory) {
+  if (!pMemory || fd < 0 || allocationSize == 0) return VK_ERROR_INITIALIZATION_FAILED;
+  const int dev = DeviceFromHandle(device);
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || dev < 0 || dev >= count) {
+    cudaGetLastError();
+    return VK_ERROR_INITIALIZATION_FAILED;
+  }
+  DeviceGuard guard(dev);
+  cudaExternalMemoryHandleDesc hd{};
+  hd.type = cudaExternalMemoryHandleTypeOpaqueFd;
+  hd.handle.fd = fd;
+  hd.size = allocationSize;
+  hd.flags = dedicated ? cudaExternalMemoryDedicated : 0;
+  cudaExternalMemory_t ext = nullptr;
+  if (cudaImportExternalMemory(&ext, &hd) != cudaSuccess) {
+    cudaGetLastError();
+    return VK_ERROR_INITIALIZATION_FAILED;
+  }
+  cudaExternalMemoryBufferDesc bd{};
+  bd.offset = 0;
+  bd.size = allocationSize;
+  void* base = nullptr;
+  if (cudaExternalMemoryGetMappedBuffer(&base, ext, &bd) != cudaSuccess) {
+    cudaGetLastError();
+    cudaDestroyExternalMemory(ext);
+    return VK_ERROR_OUT_OF_DEVICE_MEMORY;
+  }
+  VrdxCudaImportedMemory_T* m = new (std::nothrow) VrdxCudaImportedMemory_T();
+  if (!m) {
+    cudaFree(base);
+    cudaDestroyExternalMemory(ext);
+    return VK_ERROR_OUT_OF_HOST_MEMORY;
+  }
+  m->device = dev;
+  m->ext = ext;
+  m->base = base;
+  m->size = allocationSize;
+  *pMemory = m;
+  return VK_SUCCESS;
+}
+
+VkBuffer vrdxCudaImportedMemoryBuffer(VrdxCudaImportedMemory memory, VkDeviceSize memoryOffset) {
+  if (!memory || memoryOffset >= memory->size) return VK_NULL_HANDLE;
+  return reinterpret_cast<VkBuffer>(static_cast<char*>(memory->base) + memoryOffset);
+}
+
+void vrdxCudaReleaseImportedMemory(VrdxCudaImportedMemory memory) {
+  if (!memory) return;
+  DeviceGuard guard(memory->device);
+  cudaFree(memory->base);
+  cudaDestroyExternalMemory(memory->ext);
+  delete memory;
+}
+
+void vrdxCudaGetSorterProperties(VrdxSorter sorter, VrdxCudaSorterProperties* p) {
+  if (!sorter || !p) return;
+  p->deviceOrdinal = sorter->device;
+  p->smCount = sorter->sm_count;
+  p->ccMajor = sorter->cc_major;
+  p->ccMinor = sorter->cc_minor;
+  p->keysTileSize = KeysCfg::kTile;
+  p->keyValueTileSize = PairCfg::kTile;
+  p->offsetAlignment = kOffsetAlignment;
+  p->maxOnesweepCount = (uint32_t)kMaxOnesweepCount;
+}
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+"""Host-side convenience over the C-ABI: a sorter bound to one CUDA device.
+
+This is the Python twin of how the reference's own caller drives the API
+(bench/vulkan_benchmark.cc:253-433: create sorter once, query storage requirements, allocate
+storage, record vrdxCmdSort* into a command buffer, submit, wait).  PyTorch supplies device
+memory and streams only; every sort goes through ``vrdxCmdSort*`` in libvrdx_b200.so.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import api
+
+
+def _as_i32(t: torch.Tensor) -> torch.Tensor:
+    """uint32 payloads are carried in int32 tensors (same bits; torch's uint32 support is thin)."""
+    if t.dtype == torch.int32:
+        return t
+    if t.dtype == torch.uint32:
+        return t.view(torch.int32)
+    raise TypeError(f"keys/values must be 32-bit integers, got {t.dtype}")
+
+
+class Sorter:
+    """One ``VrdxSorter`` plus a grow-only storage buffer (the caller-owned scratch)."""
+
+    def __init__(self, device: int | torch.device = 0, algorithm: int = api.VRDX_CUDA_ALGORITHM_AUTO,
+                 tile_load: int = api.VRDX_CUDA_TILE_LOAD_AUTO):
+        if not torch.cuda.is_available():
+            raise RuntimeError("vulkan_radix_sort_b200 needs a CUDA device; there is no CPU fallback")
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        ordinal = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", ordinal)
+        info = api.VrdxSorterCreateInfo(api.cuda_device(ordinal), api.cuda_device(ordinal), None)
+        res, handle = api.vrdxCudaCreateSorter(info, algorithm, tile_load)
+        if res != api.VK_SUCCESS:
+            raise RuntimeError(f"vrdxCreateSorter failed with VkResult {res}")
+        self.handle = handle
+        self._storage: torch.Tensor | None = None
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            torch.cuda.synchronize(self.device)
+            api.vrdxDestroySorter(self.handle)
+            self.handle = None
+            self._storage = None
+
+    def __del__(self):  # best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ storage
+    def storage_requirements(self, max_count: int, key_value: bool = False):
+        fn = api.vrdxGetSorterKeyValueStorageRequirements if key_value else api.vrdxGetSorterStorageRequirements
+        return fn(self.handle, max_count)
+
+    def storage_for(self, max_count: int, key_value: bool) -> torch.Tensor:
+        need = self.storage_requirements(max_count, key_value).size
+        if self._storage is None or self._storage.numel() < need:
+            self._storage = None
+            self._storage = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._storage
+
+    # ------------------------------------------------------------------ sorts (in place)
+    def _stream(self, stream):
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        return s.cuda_stream
+
+    def check(self) -> None:
+        err = api.vrdxCudaGetLastError(self.handle)
+        if err:
+            raise RuntimeError(f"vrdx CUDA error {err}: {api.vrdxCudaGetErrorString(err)}")
+
+    def sort(self, keys: torch.Tensor, count: int | None = None, storage: torch.Tensor | None = None,
+             stream=None, query_pool=None, query: int = 0) -> None:
+        """vrdxCmdSort: sort keys[0:count] ascending as unsigned 32-bit, in place."""
+        k = _as_i32(keys)
+        n = k.numel() if count is None else int(count)
+        st = storage if storage is not None else self.storage_for(n, False)
+        api.vrdxCmdSort(self._stream(stream), self.handle, n, k.data_ptr(), 0, st.data_ptr(), 0,
+                        query_pool, query)
+        self.check()
+
+    def sort_key_value(self, keys: torch.Tensor, values: torch.Tensor, count: int | None = None,
+                       storage: torch.Tensor | None = None, stream=None, query_pool=None,
+                       query: int = 0) -> None:
+        """vrdxCmdSortKeyValue: stable sort of (key, value) pairs by key, in place."""
+        k, v = _as_i32(keys), _as_i32(values)
+        n = k.numel() if count is None else int(count)
+        st = storage if storage is not None else self.storage_for(n, True)
+        api.vrdxCmdSortKeyValue(self._stream(stream), self.handle, n, k.data_ptr(), 0, v.data_ptr(), 0,
+                                st.data_ptr(), 0, query_pool, query)
+        self.check()
+
+    def sort_indirect(self, keys: torch.Tensor, count_buffer: torch.Tensor, max_count: int | None = None,
+                      count_offset: int = 0, storage: torch.Tensor | None = None, stream=None,
+                      query_pool=None, query: int = 0) -> None:
+        """vrdxCmdSortIndirect: the element count is read from device memory at sort time."""
+        k = _as_i32(keys)
+        m = k.numel() if max_count is None else int(max_count)
+        st = storage if storage is not None else self.storage_for(m, False)
+        api.vrdxCmdSortIndirect(self._stream(stream), self.handle, m, count_buffer.data_ptr(), count_offset,
+                                k.data_ptr(), 0, st.data_ptr(), 0, query_pool, query)
+        self.check()
+
+    def sort_key_value_indirect(self, keys: torch.Tensor, values: torch.Tensor, count_buffer: torch.Tensor,
+                                max_count: int | None = None, count_offset: int = 0,
+                                storage: torch.Tensor | None = None, stream=None, query_pool=None,
+                                query: int = 0) -> None:
+        k, v = _as_i32(keys), _as_i32(values)
+        m = k.numel() if max_count is None else int(max_count)
+        st = storage if storage is not None else self.storage_for(m, True)
+        api.vrdxCmdSortKeyValueIndirect(self._stream(stream), self.handle, m, count_buffer.data_ptr(),
+                                        count_offset, k.data_ptr(), 0, v.data_ptr(), 0, st.data_ptr(), 0,
+                                        query_pool, query)
+        self.check()
+
+    @property
+    def properties(self):
+        return api.vrdxCudaGetSorterProperties(self.handle)
+
+    @property
+    def last_launch_count(self) -> int:
+        return api.vrdxCudaGetLastLaunchCount(self.handle)
