@@ -12,6 +12,7 @@
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -25,10 +26,49 @@
 using namespace vrdx;
 
 // ---------------------------------------------------------------------------- configuration
-// Tile shapes of the pass kernel (threads x keys per thread).  One CTA sorts one tile per pass.
-using KeysCfg = PassConfig<512, 16, false>;
-using PairCfg = PassConfig<512, 16, true>;
-constexpr uint32_t kMinTile = (KeysCfg::kTile < PairCfg::kTile) ? KeysCfg::kTile : PairCfg::kTile;
+// Tile shapes of the pass kernel: threads x keys-per-thread, and the CTAs/SM the register
+// allocation is bounded for.  One CTA sorts one tile per pass.  Several shapes are compiled in
+// so they can be A/B-measured on the device (VrdxCudaSorterOptions::reserved[0..1] or the
+// VRDX_KEYS_VARIANT / VRDX_KV_VARIANT environment variables pick one at sorter creation);
+// index 0 of each table is the tuned default.
+struct PassVariant {
+  int threads, items, min_ctas;
+  uint32_t tile;
+  size_t smem;
+  cudaError_t (*prepare)();
+  cudaError_t (*launch)(cudaStream_t, uint32_t, const PassArgs&);
+};
+
+template <class Cfg>
+cudaError_t PrepareVariant() {
+  return cudaFuncSetAttribute(OnesweepKernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)Cfg::kSmemBytes);
+}
+template <class Cfg>
+cudaError_t LaunchVariant(cudaStream_t stream, uint32_t grid, const PassArgs& args) {
+  OnesweepKernel<Cfg><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(args);
+  return cudaGetLastError();
+}
+template <int T, int I, bool KV, int M>
+constexpr PassVariant MakeVariant() {
+  using Cfg = PassConfig<T, I, KV, M>;
+  return PassVariant{T, I, M, (uint32_t)Cfg::kTile, Cfg::kSmemBytes, &PrepareVariant<Cfg>, &LaunchVariant<Cfg>};
+}
+
+static const PassVariant kKeysVariants[] = {
+    MakeVariant<512, 16, false, 2>(), MakeVariant<256, 16, false, 4>(), MakeVariant<256, 16, false, 3>(),
+    MakeVariant<384, 16, false, 2>(), MakeVariant<256, 24, false, 2>(), MakeVariant<512, 16, false, 1>(),
+    MakeVariant<256, 12, false, 5>(), MakeVariant<512, 12, false, 2>(),
+};
+static const PassVariant kPairVariants[] = {
+    MakeVariant<512, 16, true, 2>(), MakeVariant<256, 16, true, 3>(), MakeVariant<256, 16, true, 4>(),
+    MakeVariant<384, 16, true, 2>(), MakeVariant<256, 24, true, 2>(), MakeVariant<512, 16, true, 1>(),
+    MakeVariant<256, 12, true, 4>(), MakeVariant<512, 12, true, 2>(),
+};
+constexpr int kNumKeysVariants = sizeof(kKeysVariants) / sizeof(kKeysVariants[0]);
+constexpr int kNumPairVariants = sizeof(kPairVariants) / sizeof(kPairVariants[0]);
+// Smallest tile of any compiled variant: sizes the look-back buffers whichever variant runs.
+constexpr uint32_t kMinTile = 256 * 12;
 
 struct VrdxSorter_T {
   int device = 0;
@@ -36,6 +76,8 @@ struct VrdxSorter_T {
   int cc_major = 0, cc_minor = 0;
   VrdxCudaAlgorithm algorithm = VRDX_CUDA_ALGORITHM_AUTO;
   VrdxCudaTileLoad tile_load = VRDX_CUDA_TILE_LOAD_AUTO;
+  int keys_variant = 0;
+  int pair_variant = 0;
   // The only mutable words: a sticky error and a launch counter (diagnostics, not sort state).
   std::atomic<int> last_error{0};
   std::atomic<uint32_t> last_launches{0};
@@ -94,18 +136,6 @@ void Stamp(VrdxSorter s, cudaStream_t stream, VkQueryPool pool, uint32_t slot) {
   qp->recorded[slot] = 1;
 }
 
-template <typename Cfg, bool KV>
-cudaError_t PrepareKernel() {
-  return cudaFuncSetAttribute(OnesweepKernel<Cfg::kThreads, Cfg::kItems, KV>,
-                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
-}
-
-template <typename Cfg, bool KV>
-cudaError_t LaunchPass(cudaStream_t stream, uint32_t grid, const PassArgs& args) {
-  OnesweepKernel<Cfg::kThreads, Cfg::kItems, KV><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(args);
-  return cudaGetLastError();
-}
-
 // The body of every vrdxCmdSort* (reference: gpuSort, h.in:344-507).
 void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or_max,
                  VkBuffer indirectBuffer, VkDeviceSize indirectOffset, VkBuffer keysBuffer,
@@ -148,8 +178,8 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
   uint32_t* keys_alt = reinterpret_cast<uint32_t*>(storage + lay.keys_alt_offset);
   uint32_t* vals_alt = reinterpret_cast<uint32_t*>(storage + lay.values_alt_offset);
 
-  const uint32_t tile = kv ? PairCfg::kTile : KeysCfg::kTile;
-  const uint32_t tiles = (uint32_t)CeilDiv(n_or_max, tile);
+  const PassVariant& variant = kv ? kPairVariants[sorter->pair_variant] : kKeysVariants[sorter->keys_variant];
+  const uint32_t tiles = (uint32_t)CeilDiv(n_or_max, variant.tile);
 
   // Reset per-sort state inside the stream (reference: vkCmdFillBuffer of the global
   // histogram, h.in:382): header (histograms, tickets) + the pass-0 look-back cells.
@@ -185,9 +215,7 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
     // One fused kernel per pass: the reference's upsweep and spine slots collapse onto its start.
     Stamp(sorter, stream, queryPool, query + 2 + 3 * pass + 0);
     Stamp(sorter, stream, queryPool, query + 2 + 3 * pass + 1);
-    cudaError_t e = kv ? LaunchPass<PairCfg, true>(stream, tiles, args)
-                       : LaunchPass<KeysCfg, false>(stream, tiles, args);
-    NoteError(sorter, e);
+    NoteError(sorter, variant.launch(stream, tiles, args));
     ++launches;
     Stamp(sorter, stream, queryPool, query + 2 + 3 * pass + 2);
   }
@@ -219,8 +247,17 @@ VkResult vrdxCudaCreateSorter(const VrdxSorterCreateInfo* pCreateInfo,
   if (prop.major != 10) return VK_ERROR_FEATURE_NOT_PRESENT;  // kernels are built for sm_100a only
 
   DeviceGuard guard(dev);
+  int keys_variant = 0, pair_variant = 0;
+  if (const char* e = getenv("VRDX_KEYS_VARIANT")) keys_variant = atoi(e);
+  if (const char* e = getenv("VRDX_KV_VARIANT")) pair_variant = atoi(e);
+  if (pOptions && pOptions->structSize >= sizeof(VrdxCudaSorterOptions)) {
+    if (pOptions->reserved[0]) keys_variant = (int)pOptions->reserved[0] - 1;
+    if (pOptions->reserved[1]) pair_variant = (int)pOptions->reserved[1] - 1;
+  }
+  if (keys_variant < 0 || keys_variant >= kNumKeysVariants || pair_variant < 0 || pair_variant >= kNumPairVariants)
+    return VK_ERROR_INITIALIZATION_FAILED;
   // "Pipeline creation": opt the pass kernels into their shared-memory footprint.
-  if (PrepareKernel<KeysCfg, false>() != cudaSuccess || PrepareKernel<PairCfg, true>() != cudaSuccess) {
+  if (kKeysVariants[keys_variant].prepare() != cudaSuccess || kPairVariants[pair_variant].prepare() != cudaSuccess) {
     cudaGetLastError();
     return VK_ERROR_INITIALIZATION_FAILED;
   }
@@ -231,6 +268,8 @@ VkResult vrdxCudaCreateSorter(const VrdxSorterCreateInfo* pCreateInfo,
   s->sm_count = prop.multiProcessorCount;
   s->cc_major = prop.major;
   s->cc_minor = prop.minor;
+  s->keys_variant = keys_variant;
+  s->pair_variant = pair_variant;
   if (pOptions && pOptions->structSize >= sizeof(VrdxCudaSorterOptions)) {
     s->algorithm = pOptions->algorithm;
     s->tile_load = pOptions->tileLoad;
@@ -445,8 +484,8 @@ void vrdxCudaGetSorterProperties(VrdxSorter sorter, VrdxCudaSorterProperties* p)
   p->smCount = sorter->sm_count;
   p->ccMajor = sorter->cc_major;
   p->ccMinor = sorter->cc_minor;
-  p->keysTileSize = KeysCfg::kTile;
-  p->keyValueTileSize = PairCfg::kTile;
+  p->keysTileSize = kKeysVariants[sorter->keys_variant].tile;
+  p->keyValueTileSize = kPairVariants[sorter->pair_variant].tile;
   p->offsetAlignment = kOffsetAlignment;
   p->maxOnesweepCount = (uint32_t)kMaxOnesweepCount;
 }

@@ -7,11 +7,11 @@
 // with a different decomposition:
 //   HistogramKernel   ONE read of the keys builds all four 256-bin digit histograms; the last
 //                     CTA to finish exclusive-scans them in place (no separate spine launch).
-//   OnesweepKernel    one launch per pass: warp-level multi-split ranking (__match_any_sync on
-//                     the digit, warp-private shared-memory histograms, no shared atomics),
-//                     tile-local reorder through shared memory, single-pass decoupled look-back
-//                     across tiles for the digit offsets, run-wise coalesced scatter.  Keys and
-//                     values are two separate arrays end to end, as in the reference.
+//   OnesweepKernel    one launch per pass: warp-level multi-split ranking (peer masks built with
+//                     shared-memory atomicOr in warp-private cells), tile-local reorder through
+//                     shared memory, single-pass decoupled look-back across tiles for the digit
+//                     offsets, run-wise coalesced scatter.  Keys and values are two separate
+//                     arrays end to end, as in the reference.
 // Stability: a warp owns 32*IPT consecutive keys and ranks them item by item, lane by lane, so
 // (warp, item, lane) order == index order — the same argument as downsweep.slang:79-80.
 #pragma once
@@ -151,6 +151,16 @@ HistogramKernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // OnesweepKernel — one LSD pass over one tile per CTA.
 // Algorithmic traffic per pass: 4 B/key read + 4 B/key write (+ 4 + 4 for values).
+//
+// Ranking (measured on B200, tools/microbench_rank.cu, cycles per 32 keys per SM at 32 warps/SM):
+//   hardware MATCH.ANY on an 8-bit digit   60.7      (cost grows with the number of distinct values)
+//   8-round ballot loop (the reference's downsweep.slang:92-99, also CUB's choice)   28.8
+//   shared-memory atomicOr peer mask + counter cell (this kernel)   16.5
+// so the peer mask of a key (lanes of its warp holding the same digit) is built with ONE
+// shared-memory atomicOr into a warp-private cell and read back; the result is independent of
+// the order in which the hardware serialises colliding lanes, so ranks are by lane order and the
+// pass is stable.  Mask and running count of a (warp, digit) share one 8-byte cell, so a key
+// costs one ATOMS, one LDS.64 and (for the lowest peer lane only) one STS.64.
 // ------------------------------------------------------------------------------------------
 struct PassArgs {
   const uint32_t* indirect;   // device count or nullptr
@@ -165,32 +175,36 @@ struct PassArgs {
   uint32_t* vals_out;
 };
 
-template <int THREADS, int IPT, bool KV>
+template <int THREADS, int IPT, bool KV, int MIN_CTAS>
 struct PassConfig {
   static constexpr int kThreads = THREADS;
   static constexpr int kItems = IPT;
+  static constexpr int kMinCtas = MIN_CTAS;
+  static constexpr bool kKeyValue = KV;
   static constexpr int kWarps = THREADS / 32;
   static constexpr int kTile = THREADS * IPT;
   static constexpr int kMiscWords = 16;
+  // [kWarps][256] uint2 cells | keys[kTile] | vals[kTile] (KV) | gbase[256] | misc
   static constexpr size_t kSmemBytes =
-      sizeof(uint32_t) * ((size_t)kWarps * kRadix + (size_t)kTile * (KV ? 2 : 1) + 2 * kRadix + kMiscWords);
-  static_assert(THREADS % 32 == 0 && THREADS >= kRadix, "one thread per digit is assumed");
+      sizeof(uint32_t) * ((size_t)kWarps * kRadix * 2 + (size_t)kTile * (KV ? 2 : 1) + kRadix + kMiscWords);
+  static_assert(THREADS % 32 == 0 && THREADS >= kRadix && THREADS <= 1024, "one thread per digit is assumed");
   static_assert(kTile <= (1 << 16), "tile ranks are kept below 2^16");
 };
 
-template <int THREADS, int IPT, bool KV>
-__global__ void __launch_bounds__(THREADS)
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinCtas)
 OnesweepKernel(const PassArgs a) {
-  using Cfg = PassConfig<THREADS, IPT, KV>;
+  constexpr int THREADS = Cfg::kThreads;
+  constexpr int IPT = Cfg::kItems;
+  constexpr bool KV = Cfg::kKeyValue;
   constexpr int kWarps = Cfg::kWarps;
   constexpr int kTile = Cfg::kTile;
 
   extern __shared__ __align__(16) uint32_t smem[];
-  uint32_t* s_hist = smem;                            // [kWarps][256] warp-private digit counters
-  uint32_t* s_keys = s_hist + kWarps * kRadix;        // [kTile] tile reordered by digit
+  uint2* s_cell = reinterpret_cast<uint2*>(smem);     // [kWarps][256] {peer mask scratch, running count / base}
+  uint32_t* s_keys = smem + kWarps * kRadix * 2;      // [kTile] tile reordered by digit
   uint32_t* s_vals = s_keys + kTile;                  // [kTile] (KV only)
-  uint32_t* s_dbase = s_vals + (KV ? kTile : 0);      // [256] first tile-local slot of each digit
-  uint32_t* s_gbase = s_dbase + kRadix;               // [256] global slot of tile-local slot 0, per digit
+  uint32_t* s_gbase = s_vals + (KV ? kTile : 0);      // [256] global slot of tile-local slot 0, per digit
   uint32_t* s_misc = s_gbase + kRadix;                // [0..7] warp totals, [8] tile id
 
   const int tid = threadIdx.x;
@@ -202,9 +216,11 @@ OnesweepKernel(const PassArgs a) {
   // Tile ids are handed out in arrival order so that every predecessor a tile may wait on in
   // the look-back is already resident (forward progress without relying on blockIdx order).
   if (tid == 0) s_misc[8] = atomicAdd(&a.hdr->tickets[a.pass], 1u);
-  uint32_t* wh = s_hist + warp * kRadix;
+  {
+    uint4* z = reinterpret_cast<uint4*>(s_cell);
 #pragma unroll
-  for (int j = 0; j < kRadix / 32; ++j) wh[lane + 32 * j] = 0;
+    for (int j = tid; j < kWarps * kRadix / 2; j += THREADS) z[j] = make_uint4(0u, 0u, 0u, 0u);
+  }
   __syncthreads();
 
   const uint32_t tile = s_misc[8];
@@ -218,84 +234,94 @@ OnesweepKernel(const PassArgs a) {
 
   // ---- load: warp-striped, 128 B per warp-instruction -------------------------------------
   uint32_t key[IPT];
-  uint32_t val[KV ? IPT : 1];
   const uint32_t woff = warp * 32 * IPT + lane;
   {
     const uint32_t* kin = a.keys_in + tile_start + woff;
-    const uint32_t* vin = KV ? a.vals_in + tile_start + woff : nullptr;
     if (full) {
 #pragma unroll
       for (int i = 0; i < IPT; ++i) key[i] = LdStream(kin + 32 * i);
-      if (KV) {
-#pragma unroll
-        for (int i = 0; i < IPT; ++i) val[i] = LdStream(vin + 32 * i);
-      }
     } else {
       // Tail tile: pad with the largest key so pads rank after every real key (the reference
       // pads the same way, downsweep.slang:81,85); their slots are >= tile_count and never stored.
 #pragma unroll
       for (int i = 0; i < IPT; ++i) key[i] = (woff + 32 * i < tile_count) ? LdStream(kin + 32 * i) : 0xFFFFFFFFu;
-      if (KV) {
-#pragma unroll
-        for (int i = 0; i < IPT; ++i) val[i] = (woff + 32 * i < tile_count) ? LdStream(vin + 32 * i) : 0u;
-      }
     }
   }
 
   // ---- warp-level multi-split: rank of each key among equal digits inside its warp ---------
   uint32_t rank[IPT];
-  const uint32_t lt = LaneMaskLt();
+  {
+    uint2* cell = s_cell + warp * kRadix;
+    const uint32_t lt = LaneMaskLt();
+    const uint32_t lanebit = 1u << lane;
 #pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const uint32_t d = (key[i] >> shift) & 0xFFu;
-    const uint32_t peers = __match_any_sync(0xffffffffu, d);
-    const uint32_t before = wh[d];
-    const uint32_t below = __popc(peers & lt);
-    __syncwarp();
-    if (below == 0) wh[d] = before + __popc(peers);
-    __syncwarp();
-    rank[i] = before + below;
+    for (int i = 0; i < IPT; ++i) {
+      const uint32_t d = (key[i] >> shift) & 0xFFu;
+      atomicOr(&cell[d].x, lanebit);
+      __syncwarp();
+      const uint2 pc = cell[d];  // {peers of this key in the warp, count of digit d in earlier items}
+      const uint32_t below = __popc(pc.x & lt);
+      __syncwarp();
+      if (below == 0) cell[d] = make_uint2(0u, pc.y + __popc(pc.x));  // lowest peer clears the mask, bumps the count
+      __syncwarp();
+      rank[i] = pc.y + below;
+    }
   }
   __syncthreads();
 
   // ---- per-digit: counts over warps, publish aggregate, tile-local exclusive scan -----------
-  uint32_t digit_count = 0, digit_incl = 0;
+  uint32_t digit_count = 0, digit_excl = 0;
+  uint32_t wcount[kWarps];
   if (tid < kRadix) {
     uint32_t sum = 0;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) {
-      const uint32_t c = s_hist[w * kRadix + tid];
-      s_hist[w * kRadix + tid] = sum;  // exclusive over warps
-      sum += c;
+      wcount[w] = s_cell[w * kRadix + tid].y;
+      sum += wcount[w];
     }
-    digit_incl = WarpInclusiveScan(sum, lane);
-    if (lane == 31) s_misc[warp] = digit_incl;
     // pads were counted as digit 255; they are not part of the data
     digit_count = sum - ((tid == kRadix - 1) ? ((uint32_t)kTile - tile_count) : 0u);
     StRelaxed(a.status + (size_t)tile * kRadix + tid,
               (tile == 0 ? kStatusPrefix : kStatusAggregate) | digit_count);
-    digit_incl -= sum;  // exclusive within the warp
+    const uint32_t incl = WarpInclusiveScan(sum, lane);
+    if (lane == 31) s_misc[warp] = incl;
+    digit_excl = incl - sum;  // exclusive within the warp
   }
   __syncthreads();
   uint32_t first_look = 0;
   if (tid < kRadix) {
-    uint32_t prefix = 0;
 #pragma unroll
-    for (int w = 0; w < kRadix / 32; ++w) prefix += (w < warp) ? s_misc[w] : 0u;
-    s_dbase[tid] = digit_incl + prefix;
-    digit_incl += prefix;
+    for (int w = 0; w < kRadix / 32; ++w) digit_excl += (w < warp) ? s_misc[w] : 0u;
+    // cell.y becomes the tile-local slot of the first key of (warp, digit)
+    uint32_t run = digit_excl;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      s_cell[w * kRadix + tid].y = run;
+      run += wcount[w];
+    }
     // start the first look-back load now; it is consumed after the reorder below
     if (tile > 0) first_look = LdRelaxed(a.status + (size_t)(tile - 1) * kRadix + tid);
   }
   __syncthreads();
 
   // ---- tile-local reorder through shared memory --------------------------------------------
+  {
+    const uint2* cell = s_cell + warp * kRadix;
 #pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const uint32_t d = (key[i] >> shift) & 0xFFu;
-    const uint32_t r = rank[i] + wh[d] + s_dbase[d];
-    s_keys[r] = key[i];
-    if (KV) s_vals[r] = val[i];
+    for (int i = 0; i < IPT; ++i) {
+      const uint32_t d = (key[i] >> shift) & 0xFFu;
+      rank[i] += cell[d].y;
+      s_keys[rank[i]] = key[i];
+    }
+    if (KV) {
+      // values are fetched only now, so they do not occupy registers during the ranking
+      const uint32_t* vin = a.vals_in + tile_start + woff;
+      uint32_t val[IPT];
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) val[i] = (full || woff + 32 * i < tile_count) ? LdStream(vin + 32 * i) : 0u;
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) s_vals[rank[i]] = val[i];
+    }
   }
 
   // ---- decoupled look-back: exclusive prefix of this digit over all earlier tiles ------------
@@ -315,7 +341,7 @@ OnesweepKernel(const PassArgs a) {
       StRelaxed(a.status + (size_t)tile * kRadix + tid, kStatusPrefix | (excl + digit_count));
     }
     // global slot of tile-local slot 0 for this digit (mod 2^32 arithmetic)
-    s_gbase[tid] = a.hdr->global_hist[a.pass][tid] + excl - digit_incl;
+    s_gbase[tid] = a.hdr->global_hist[a.pass][tid] + excl - digit_excl;
   }
   __syncthreads();
 
