@@ -78,7 +78,7 @@ def test_storage_requirements_are_pure_host_arithmetic(lib):
         assert k.size >= prev_k and kv.size >= prev_kv         # monotone in N
         prev_k, prev_kv = k.size, kv.size
     # same order of magnitude as the reference's own scratch (h.in:279-308) at N=2^28: 1,140,854,816 B
-    assert api.vrdxGetSorterStorageRequirements(None, 1 << 28).size < 1_140_854_816 * 1.05
+    assert api.vrdxGetSorterStorageRequirements(None, 1 << 28).size < 1_140_854_816 * 1.10
 
 
 def test_create_sorter_error_paths(lib):

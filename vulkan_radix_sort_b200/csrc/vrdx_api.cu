@@ -56,19 +56,19 @@ constexpr PassVariant MakeVariant() {
 }
 
 static const PassVariant kKeysVariants[] = {
-    MakeVariant<512, 16, false, 2>(), MakeVariant<256, 16, false, 4>(), MakeVariant<256, 16, false, 3>(),
-    MakeVariant<384, 16, false, 2>(), MakeVariant<256, 24, false, 2>(), MakeVariant<512, 16, false, 1>(),
-    MakeVariant<256, 12, false, 5>(), MakeVariant<512, 12, false, 2>(),
+    MakeVariant<384, 16, false, 3>(), MakeVariant<256, 16, false, 4>(), MakeVariant<512, 16, false, 2>(),
+    MakeVariant<320, 16, false, 3>(), MakeVariant<512, 12, false, 2>(), MakeVariant<1024, 8, false, 1>(),
+    MakeVariant<512, 8, false, 3>(), MakeVariant<768, 12, false, 1>(),
 };
 static const PassVariant kPairVariants[] = {
-    MakeVariant<512, 16, true, 2>(), MakeVariant<256, 16, true, 3>(), MakeVariant<256, 16, true, 4>(),
-    MakeVariant<384, 16, true, 2>(), MakeVariant<256, 24, true, 2>(), MakeVariant<512, 16, true, 1>(),
-    MakeVariant<256, 12, true, 4>(), MakeVariant<512, 12, true, 2>(),
+    MakeVariant<384, 16, true, 3>(), MakeVariant<256, 16, true, 4>(), MakeVariant<512, 16, true, 2>(),
+    MakeVariant<320, 16, true, 3>(), MakeVariant<512, 12, true, 2>(), MakeVariant<1024, 8, true, 1>(),
+    MakeVariant<512, 8, true, 3>(), MakeVariant<768, 12, true, 1>(),
 };
 constexpr int kNumKeysVariants = sizeof(kKeysVariants) / sizeof(kKeysVariants[0]);
 constexpr int kNumPairVariants = sizeof(kPairVariants) / sizeof(kPairVariants[0]);
 // Smallest tile of any compiled variant: sizes the look-back buffers whichever variant runs.
-constexpr uint32_t kMinTile = 256 * 12;
+constexpr uint32_t kMinTile = 4096;
 
 struct VrdxSorter_T {
   int device = 0;

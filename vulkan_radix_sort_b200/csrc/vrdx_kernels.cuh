@@ -7,10 +7,11 @@
 // with a different decomposition:
 //   HistogramKernel   ONE read of the keys builds all four 256-bin digit histograms; the last
 //                     CTA to finish exclusive-scans them in place (no separate spine launch).
-//   OnesweepKernel    one launch per pass: warp-level multi-split ranking (peer masks built with
-//                     shared-memory atomicOr in warp-private cells), tile-local reorder through
-//                     shared memory, single-pass decoupled look-back across tiles for the digit
-//                     offsets, run-wise coalesced scatter.  Keys and values are two separate
+//   OnesweepKernel    one launch per pass: warp-level multi-split ranking (optimistic returning
+//                     shared-memory atomicAdd on warp-private counters + lane-ordered repair of
+//                     collisions), tile-local reorder through shared memory, single-pass
+//                     decoupled look-back across tiles for the digit offsets, run-wise coalesced
+//                     scatter.  Keys and values are two separate
 //                     arrays end to end, as in the reference.
 // Stability: a warp owns 32*IPT consecutive keys and ranks them item by item, lane by lane, so
 // (warp, item, lane) order == index order — the same argument as downsweep.slang:79-80.
@@ -152,15 +153,22 @@ HistogramKernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ 
 // OnesweepKernel — one LSD pass over one tile per CTA.
 // Algorithmic traffic per pass: 4 B/key read + 4 B/key write (+ 4 + 4 for values).
 //
-// Ranking (measured on B200, tools/microbench_rank.cu, cycles per 32 keys per SM at 32 warps/SM):
-//   hardware MATCH.ANY on an 8-bit digit   60.7      (cost grows with the number of distinct values)
-//   8-round ballot loop (the reference's downsweep.slang:92-99, also CUB's choice)   28.8
-//   shared-memory atomicOr peer mask + counter cell (this kernel)   16.5
-// so the peer mask of a key (lanes of its warp holding the same digit) is built with ONE
-// shared-memory atomicOr into a warp-private cell and read back; the result is independent of
-// the order in which the hardware serialises colliding lanes, so ranks are by lane order and the
-// pass is stable.  Mask and running count of a (warp, digit) share one 8-byte cell, so a key
-// costs one ATOMS, one LDS.64 and (for the lowest peer lane only) one STS.64.
+// Ranking.  Measured on B200 (tools/microbench_rank.cu; cycles per 32 keys per SM, 32 warps/SM):
+//   hardware MATCH.ANY on an 8-bit digit                                   60.7
+//   8-round ballot loop (reference downsweep.slang:92-99; CUB's choice)    28.8
+//   shared-memory atomicOr peer mask + counter cell                        16.5
+//   shared-memory atomicAdd (returning) on a warp-private counter           4.0
+// and the first full kernel built on atomicOr cells was bound by the shared-memory pipe
+// (profiles/: l1tex 77 % busy, 31 wavefronts per 32 keys).  So the rank of a key among equal
+// digits of its warp is computed OPTIMISTICALLY: every lane does one returning atomicAdd(+1) on
+// the warp-private counter of its digit.  A lane that is alone with its digit in this
+// warp-instruction (89 % of lanes on uniform keys) gets its rank straight from the returned
+// value.  Lanes that collided are served by the hardware in an unspecified order, so they are
+// detected (counter read-back: more than one increment landed after my returned value) and
+// REPAIRED in lane order: one shuffle + one ballot per collision group (1.8 groups per 32 uniform
+// keys).  If many lanes collide (low-entropy digits) the repair switches to the fixed 8-round
+// ballot loop.  Ranks are therefore exactly those of a stable counting sort whatever order the
+// hardware serialises colliding atomics in.
 // ------------------------------------------------------------------------------------------
 struct PassArgs {
   const uint32_t* indirect;   // device count or nullptr
@@ -175,6 +183,9 @@ struct PassArgs {
   uint32_t* vals_out;
 };
 
+constexpr int kLookBatch = 4;          // look-back cells fetched per round trip
+constexpr int kRepairBallotThreshold = 12;  // colliding lanes above which the 8-round ballot loop is cheaper
+
 template <int THREADS, int IPT, bool KV, int MIN_CTAS>
 struct PassConfig {
   static constexpr int kThreads = THREADS;
@@ -184,9 +195,9 @@ struct PassConfig {
   static constexpr int kWarps = THREADS / 32;
   static constexpr int kTile = THREADS * IPT;
   static constexpr int kMiscWords = 16;
-  // [kWarps][256] uint2 cells | keys[kTile] | vals[kTile] (KV) | gbase[256] | misc
+  // cnt[kWarps][256] | keys[kTile] | vals[kTile] (KV) | gbase[256] | misc
   static constexpr size_t kSmemBytes =
-      sizeof(uint32_t) * ((size_t)kWarps * kRadix * 2 + (size_t)kTile * (KV ? 2 : 1) + kRadix + kMiscWords);
+      sizeof(uint32_t) * ((size_t)kWarps * kRadix + (size_t)kTile * (KV ? 2 : 1) + kRadix + kMiscWords);
   static_assert(THREADS % 32 == 0 && THREADS >= kRadix && THREADS <= 1024, "one thread per digit is assumed");
   static_assert(kTile <= (1 << 16), "tile ranks are kept below 2^16");
 };
@@ -201,8 +212,8 @@ OnesweepKernel(const PassArgs a) {
   constexpr int kTile = Cfg::kTile;
 
   extern __shared__ __align__(16) uint32_t smem[];
-  uint2* s_cell = reinterpret_cast<uint2*>(smem);     // [kWarps][256] {peer mask scratch, running count / base}
-  uint32_t* s_keys = smem + kWarps * kRadix * 2;      // [kTile] tile reordered by digit
+  uint32_t* s_cnt = smem;                             // [kWarps][256] warp-private digit counters, later slot bases
+  uint32_t* s_keys = s_cnt + kWarps * kRadix;         // [kTile] tile reordered by digit
   uint32_t* s_vals = s_keys + kTile;                  // [kTile] (KV only)
   uint32_t* s_gbase = s_vals + (KV ? kTile : 0);      // [256] global slot of tile-local slot 0, per digit
   uint32_t* s_misc = s_gbase + kRadix;                // [0..7] warp totals, [8] tile id
@@ -217,9 +228,9 @@ OnesweepKernel(const PassArgs a) {
   // the look-back is already resident (forward progress without relying on blockIdx order).
   if (tid == 0) s_misc[8] = atomicAdd(&a.hdr->tickets[a.pass], 1u);
   {
-    uint4* z = reinterpret_cast<uint4*>(s_cell);
+    uint4* z = reinterpret_cast<uint4*>(s_cnt);
 #pragma unroll
-    for (int j = tid; j < kWarps * kRadix / 2; j += THREADS) z[j] = make_uint4(0u, 0u, 0u, 0u);
+    for (int j = tid; j < kWarps * kRadix / 4; j += THREADS) z[j] = make_uint4(0u, 0u, 0u, 0u);
   }
   __syncthreads();
 
@@ -251,20 +262,39 @@ OnesweepKernel(const PassArgs a) {
   // ---- warp-level multi-split: rank of each key among equal digits inside its warp ---------
   uint32_t rank[IPT];
   {
-    uint2* cell = s_cell + warp * kRadix;
+    uint32_t* cnt = s_cnt + warp * kRadix;
     const uint32_t lt = LaneMaskLt();
-    const uint32_t lanebit = 1u << lane;
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
       const uint32_t d = (key[i] >> shift) & 0xFFu;
-      atomicOr(&cell[d].x, lanebit);
+      const uint32_t old = atomicAdd(&cnt[d], 1u);   // optimistic: exact if no other lane holds digit d
       __syncwarp();
-      const uint2 pc = cell[d];  // {peers of this key in the warp, count of digit d in earlier items}
-      const uint32_t below = __popc(pc.x & lt);
+      const uint32_t fin = cnt[d];                   // all 32 increments of this item have landed
+      uint32_t r = old;
+      uint32_t suspects = __ballot_sync(0xffffffffu, fin - old > 1u);  // someone was served after me
+      if (suspects != 0u) {                                            // warp-uniform
+        if (__popc(suspects) > kRepairBallotThreshold) {
+          // many collisions (low-entropy digit): fixed-cost peer masks for every lane
+          uint32_t peers = 0xffffffffu;
+#pragma unroll
+          for (int b = 0; b < kRadixBits; ++b) {
+            const bool bit = (d >> b) & 1u;
+            const uint32_t m = __ballot_sync(0xffffffffu, bit);
+            peers &= bit ? m : ~m;
+          }
+          r = fin - __popc(peers) + __popc(peers & lt);
+        } else {
+          // few collision groups: repair them one by one, in lane order
+          do {
+            const uint32_t dstar = __shfl_sync(0xffffffffu, d, __ffs(suspects) - 1);
+            const uint32_t peers = __ballot_sync(0xffffffffu, d == dstar);
+            if (d == dstar) r = fin - __popc(peers) + __popc(peers & lt);
+            suspects &= ~peers;
+          } while (suspects != 0u);
+        }
+      }
+      rank[i] = r;
       __syncwarp();
-      if (below == 0) cell[d] = make_uint2(0u, pc.y + __popc(pc.x));  // lowest peer clears the mask, bumps the count
-      __syncwarp();
-      rank[i] = pc.y + below;
     }
   }
   __syncthreads();
@@ -276,7 +306,7 @@ OnesweepKernel(const PassArgs a) {
     uint32_t sum = 0;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) {
-      wcount[w] = s_cell[w * kRadix + tid].y;
+      wcount[w] = s_cnt[w * kRadix + tid];
       sum += wcount[w];
     }
     // pads were counted as digit 255; they are not part of the data
@@ -288,29 +318,33 @@ OnesweepKernel(const PassArgs a) {
     digit_excl = incl - sum;  // exclusive within the warp
   }
   __syncthreads();
-  uint32_t first_look = 0;
+  uint32_t look_s[kLookBatch];
   if (tid < kRadix) {
 #pragma unroll
     for (int w = 0; w < kRadix / 32; ++w) digit_excl += (w < warp) ? s_misc[w] : 0u;
-    // cell.y becomes the tile-local slot of the first key of (warp, digit)
+    // s_cnt becomes the tile-local slot of the first key of (warp, digit)
     uint32_t run = digit_excl;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) {
-      s_cell[w * kRadix + tid].y = run;
+      s_cnt[w * kRadix + tid] = run;
       run += wcount[w];
     }
-    // start the first look-back load now; it is consumed after the reorder below
-    if (tile > 0) first_look = LdRelaxed(a.status + (size_t)(tile - 1) * kRadix + tid);
+    // start the first batch of look-back loads now; it is consumed after the reorder below
+#pragma unroll
+    for (int j = 0; j < kLookBatch; ++j) {
+      const uint32_t t = (tile > (uint32_t)j) ? tile - 1 - j : 0u;
+      look_s[j] = (tile > 0) ? LdRelaxed(a.status + (size_t)t * kRadix + tid) : 0u;
+    }
   }
   __syncthreads();
 
   // ---- tile-local reorder through shared memory --------------------------------------------
   {
-    const uint2* cell = s_cell + warp * kRadix;
+    const uint32_t* base = s_cnt + warp * kRadix;
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
       const uint32_t d = (key[i] >> shift) & 0xFFu;
-      rank[i] += cell[d].y;
+      rank[i] += base[d];
       s_keys[rank[i]] = key[i];
     }
     if (KV) {
@@ -325,18 +359,30 @@ OnesweepKernel(const PassArgs a) {
   }
 
   // ---- decoupled look-back: exclusive prefix of this digit over all earlier tiles ------------
+  // kLookBatch predecessor cells are in flight per round trip; they are consumed strictly in
+  // order (nearest tile first) and the walk stops at the first inclusive prefix.
   if (tid < kRadix) {
     uint32_t excl = 0;
     if (tile > 0) {
-      uint32_t look = tile - 1;
-      uint32_t s = first_look;
-      while (true) {
-        if ((s >> 30) != 0u) {
+      uint32_t look = tile - 1;  // nearest tile not yet consumed
+      bool done = false;
+      while (!done) {
+#pragma unroll
+        for (int j = 0; j < kLookBatch; ++j) {
+          if (done) break;
+          const uint32_t s = look_s[j];
+          if ((s >> 30) == 0u) break;  // not published yet: re-poll from `look`
           excl += s & kStatusValueMask;
-          if (s & kStatusPrefix) break;
+          if (s & kStatusPrefix) { done = true; break; }
           --look;  // tile 0 always publishes a prefix, so this never underflows
         }
-        s = LdRelaxed(a.status + (size_t)look * kRadix + tid);
+        if (!done) {
+#pragma unroll
+          for (int j = 0; j < kLookBatch; ++j) {
+            const uint32_t t = (look >= (uint32_t)j) ? look - j : 0u;
+            look_s[j] = LdRelaxed(a.status + (size_t)t * kRadix + tid);
+          }
+        }
       }
       StRelaxed(a.status + (size_t)tile * kRadix + tid, kStatusPrefix | (excl + digit_count));
     }
