@@ -78,7 +78,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -233,12 +233,11 @@ def run_single(args):
     pristine = torch.from_numpy(host_keys.view(np.int32)).cuda()
     peak, peak_src = measured_peak_gbs()
 
-    sampler = ClockSampler(0)
+    sampler = ClockSampler(0)   # runs across warm-up, the timed steps and the e2e steps
     sampler.start()
     torch.cuda.synchronize()
     ms, pass_ms, launches, work, _ = time_resident(sorter, torch, api, pristine, n, False, steps, warmup)
     torch.cuda.synchronize()
-    clocks = sampler.stop()
     ms_per_step = sum(ms) / len(ms)
     value = n / (ms_per_step * 1e-3) / 1e9
 
@@ -252,6 +251,7 @@ def run_single(args):
     e2e_ms, pinned_out = time_e2e(sorter, torch, host_keys, n, max(3, min(steps, 10)), 3)
     e2e_ms_per_step = sum(e2e_ms) / len(e2e_ms)
     e2e_value = n / (e2e_ms_per_step * 1e-3) / 1e9
+    clocks = sampler.stop()
     assert cpu_oracle.is_sorted(pinned_out.numpy().view(np.uint32))
     del pinned_out
 
