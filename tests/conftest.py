@@ -30,3 +30,29 @@ def sorter():
     s = Sorter(0)
     yield s
     s.close()
+
+
+FLAVOURS = {
+    # name: (algorithm, tile_load, reserved variant selectors)
+    "onesweep": ("ONESWEEP", "DIRECT", None),
+    "reduce_then_scan": ("REDUCE_THEN_SCAN", "DIRECT", None),
+    "onesweep_tma_persistent": ("ONESWEEP", "TMA", None),
+    "reduce_then_scan_tma_persistent": ("REDUCE_THEN_SCAN", "TMA", None),
+    "onesweep_cluster4_lookback": ("ONESWEEP", "DIRECT", (7, 7)),   # kKeysVariants[6] / kPairVariants[6]
+    "auto": ("AUTO", "AUTO", None),
+}
+
+
+@pytest.fixture(scope="session", params=list(FLAVOURS))
+def any_sorter(request):
+    """Every algorithm / tile-load flavour the library ships, each through the same C-ABI."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from vulkan_radix_sort_b200 import Sorter, api
+    algo, load, reserved = FLAVOURS[request.param]
+    s = Sorter(0, algorithm=getattr(api, "VRDX_CUDA_ALGORITHM_" + algo),
+               tile_load=getattr(api, "VRDX_CUDA_TILE_LOAD_" + load), reserved=reserved)
+    s.kind = request.param
+    yield s
+    s.close()

@@ -65,7 +65,8 @@ def test_golden_vectors_from_reference(sorter):
 
 # ------------------------------------------------------------------ small-N functional sweep
 
-def test_small_n_sweep_keys_and_pairs(sorter, oracle):
+def test_small_n_sweep_keys_and_pairs(any_sorter, oracle):
+    sorter = any_sorter
     tk, tkv = tile_sizes(sorter)
     sizes = {1, 2, 3, 31, 32, 33, 255, 256, 257, 511, 512, 513, 4095, 4096, 4097,
              tk - 1, tk, tk + 1, tkv - 1, tkv, tkv + 1, 2 * tk + 1, 3 * tkv - 5, 262143, 1 << 18}
@@ -87,7 +88,8 @@ def test_zero_elements_is_a_noop(sorter):
 
 
 @pytest.mark.parametrize("dist", DISTRIBUTIONS)
-def test_distributions_bit_exact(sorter, oracle, dist):
+def test_distributions_bit_exact(any_sorter, oracle, dist):
+    sorter = any_sorter
     for n in (100003, (1 << 20) + 17):
         k = make_keys(dist, n, seed=21)
         v = np.arange(n, dtype=np.uint32)  # identity payload makes stability directly visible
@@ -122,7 +124,8 @@ def test_live_reference_when_available(sorter, oracle):
 # ------------------------------------------------------------------ indirect variants
 
 @pytest.mark.parametrize("count_frac", [1.0, 0.5, 0.0003, 0.0])
-def test_indirect_count_below_max_leaves_tail_untouched(sorter, oracle, count_frac):
+def test_indirect_count_below_max_leaves_tail_untouched(any_sorter, oracle, count_frac):
+    sorter = any_sorter
     mx = 300007
     count = int(mx * count_frac)
     k, v = DataGenerator(31).generate(mx)
@@ -195,7 +198,8 @@ def test_four_byte_aligned_key_pointer(sorter, oracle):
 
 # ------------------------------------------------------------------ API behaviour
 
-def test_storage_reuse_across_sizes_and_kinds(sorter, oracle):
+def test_storage_reuse_across_sizes_and_kinds(any_sorter, oracle):
+    sorter = any_sorter
     # one storage buffer, sized for the largest sort, reused uninitialised (garbage-filled) by
     # smaller sorts of both kinds — the sort must reset all of its own state in-stream.
     big = 400001
@@ -236,7 +240,8 @@ def test_concurrent_streams_with_distinct_storage(sorter, oracle):
         assert np.array_equal(to_np(dk), ek) and np.array_equal(to_np(dv), ev)
 
 
-def test_cuda_graph_capture_and_replay(sorter, oracle):
+def test_cuda_graph_capture_and_replay(any_sorter, oracle):
+    sorter = any_sorter
     # "record once, replay many": the enqueue must be capture-safe (no host sync, no host reads)
     n = 150001
     k1, v1 = DataGenerator(51).generate(n)
@@ -302,6 +307,39 @@ def _property_check(oracle, k_in, k_out, v_out=None):
         assert oracle.multiset_fingerprint(k_in) == oracle.multiset_fingerprint(k_out)
     else:
         assert oracle.check_stable_permutation(k_in, k_out, v_out)
+
+
+def test_all_flavours_agree_at_2_pow_25(any_sorter, oracle):
+    n = 1 << 25
+    k, v = DataGenerator(2).generate(n)
+    ok, ov = gpu_sort_kv(any_sorter, k, v)
+    ek, ev = oracle.sort_key_value(k, v)
+    assert np.array_equal(ok, ek) and np.array_equal(ov, ev)
+
+
+def test_count_of_2_pow_30_and_above_uses_32bit_counts(sorter, oracle):
+    # above the 30-bit look-back cells the library switches to reduce-then-scan on its own
+    # (the reference's size arithmetic wraps here, src/vk_radix_sort.h.in:105-114)
+    n = (1 << 30) + 12345
+    free, _ = torch.cuda.mem_get_info()
+    if free < 12 * (1 << 30):
+        pytest.skip("not enough device memory")
+    g = torch.Generator(device=DEV)
+    g.manual_seed(7)
+    dk = torch.randint(-(1 << 31), (1 << 31) - 1, (n,), dtype=torch.int32, device=DEV, generator=g)
+    ref_sum = int(dk.to(torch.int64).sum().item())
+    sorter.sort(dk)
+    torch.cuda.synchronize()
+    u = dk.view(torch.uint32)
+    assert int(dk.to(torch.int64).sum().item()) == ref_sum
+    # sortedness on the device in slices (unsigned compare through int64)
+    step = 1 << 27
+    for a in range(0, n - 1, step):
+        b = min(n, a + step + 1)
+        w = u[a:b].to(torch.int64)
+        assert bool((w[1:] >= w[:-1]).all())
+    del dk, u
+    torch.cuda.empty_cache()
 
 
 @pytest.mark.parametrize("log2n", [25, 28])

@@ -126,11 +126,15 @@ def vrdxCreateSorter(create_info: VrdxSorterCreateInfo):
 
 
 def vrdxCudaCreateSorter(create_info: VrdxSorterCreateInfo, algorithm=VRDX_CUDA_ALGORITHM_AUTO,
-                         tile_load=VRDX_CUDA_TILE_LOAD_AUTO):
+                         tile_load=VRDX_CUDA_TILE_LOAD_AUTO, reserved=None):
+    """``reserved``: optional kernel-variant selectors for A/B runs (index + 1; 0 = default):
+    [0] keys onesweep, [1] pairs onesweep, [2] keys TMA, [3] pairs TMA, [4] reduce-then-scan."""
     opts = VrdxCudaSorterOptions()
     opts.structSize = ctypes.sizeof(VrdxCudaSorterOptions)
     opts.algorithm = algorithm
     opts.tileLoad = tile_load
+    for i, v in enumerate(reserved or ()):
+        opts.reserved[i] = int(v)
     sorter = c_void_p()
     res = load_library().vrdxCudaCreateSorter(byref(create_info), byref(opts), byref(sorter))
     return res, (sorter.value if res == VK_SUCCESS else None)

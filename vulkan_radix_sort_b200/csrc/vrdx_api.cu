@@ -33,42 +33,138 @@ using namespace vrdx;
 // index 0 of each table is the tuned default.
 struct PassVariant {
   int threads, items, min_ctas;
+  bool tma;     // persistent kernel with cp.async.bulk tile staging (needs 16-byte aligned buffers)
+  int cluster;  // CTAs per thread-block cluster sharing one look-back (0: per-tile look-back)
   uint32_t tile;
   size_t smem;
-  cudaError_t (*prepare)();
-  cudaError_t (*launch)(cudaStream_t, uint32_t, const PassArgs&);
+  cudaError_t (*prepare)(int* ctas_per_sm);
+  cudaError_t (*launch)(cudaStream_t, uint32_t, const PassArgs&);          // onesweep pass
+  cudaError_t (*launch_downsweep)(cudaStream_t, uint32_t, const PassArgs&);  // reduce-then-scan: scatter pass
+  cudaError_t (*launch_upsweep)(cudaStream_t, uint32_t, const PassArgs&);    // reduce-then-scan: tile histograms
+  cudaError_t (*launch_inorder)(cudaStream_t, uint32_t, const PassArgs&);    // onesweep, tile id = blockIdx.x (experiment)
 };
 
 template <class Cfg>
-cudaError_t PrepareVariant() {
-  return cudaFuncSetAttribute(OnesweepKernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)Cfg::kSmemBytes);
+cudaError_t PrepareDirect(int* ctas_per_sm) {
+  cudaError_t e = cudaFuncSetAttribute(OnesweepKernel<Cfg, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Cfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(OnesweepKernel<Cfg, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)Cfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(OnesweepKernel<Cfg, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)Cfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, OnesweepKernel<Cfg, 0>, Cfg::kThreads,
+                                                       Cfg::kSmemBytes);
 }
 template <class Cfg>
-cudaError_t LaunchVariant(cudaStream_t stream, uint32_t grid, const PassArgs& args) {
-  OnesweepKernel<Cfg><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(args);
+cudaError_t PrepareTma(int* ctas_per_sm) {
+  cudaError_t e = cudaFuncSetAttribute(OnesweepTmaKernel<Cfg, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Cfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(OnesweepTmaKernel<Cfg, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)Cfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, OnesweepTmaKernel<Cfg, 1>, Cfg::kThreads,
+                                                       Cfg::kSmemBytes);
+}
+template <class Cfg, int MODE>
+cudaError_t LaunchDirect(cudaStream_t stream, uint32_t grid, const PassArgs& args) {
+  OnesweepKernel<Cfg, MODE><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(args);
   return cudaGetLastError();
 }
-template <int T, int I, bool KV, int M>
+template <class Cfg, int MODE>
+cudaError_t LaunchTma(cudaStream_t stream, uint32_t grid, const PassArgs& args) {
+  OnesweepTmaKernel<Cfg, MODE><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(args);
+  return cudaGetLastError();
+}
+template <class Cfg>
+cudaError_t LaunchUpsweep(cudaStream_t stream, uint32_t grid, const PassArgs& args) {
+  UpsweepKernel<256, Cfg::kTile><<<grid, 256, 0, stream>>>(args.indirect, args.n_or_max, args.pass, args.keys_in,
+                                                          args.status);
+  return cudaGetLastError();
+}
+template <int T, int I, bool KV, int M, int LB = 4>
 constexpr PassVariant MakeVariant() {
-  using Cfg = PassConfig<T, I, KV, M>;
-  return PassVariant{T, I, M, (uint32_t)Cfg::kTile, Cfg::kSmemBytes, &PrepareVariant<Cfg>, &LaunchVariant<Cfg>};
+  using Cfg = PassConfig<T, I, KV, M, LB>;
+  return PassVariant{T, I, M, false, 0, (uint32_t)Cfg::kTile, Cfg::kSmemBytes, &PrepareDirect<Cfg>,
+                     &LaunchDirect<Cfg, 0>, &LaunchDirect<Cfg, 1>, &LaunchUpsweep<Cfg>, &LaunchDirect<Cfg, 2>};
+}
+template <class Cfg, int C>
+cudaError_t PrepareCluster(int* ctas_per_sm) {
+  cudaError_t e = cudaFuncSetAttribute(OnesweepClusterKernel<Cfg, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Cfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(OnesweepKernel<Cfg, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  *ctas_per_sm = Cfg::kMinCtas;
+  return cudaSuccess;
+}
+template <class Cfg, int C>
+cudaError_t LaunchCluster(cudaStream_t stream, uint32_t grid, const PassArgs& args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);  // a multiple of C
+  cfg.blockDim = dim3(Cfg::kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, OnesweepClusterKernel<Cfg, C>, args);
+}
+template <int T, int I, bool KV, int M, int C, int LB = 4>
+constexpr PassVariant MakeClusterVariant() {
+  using Cfg = PassConfig<T, I, KV, M, LB>;
+  return PassVariant{T, I, M, false, C, (uint32_t)Cfg::kTile, Cfg::kSmemBytes, &PrepareCluster<Cfg, C>,
+                     &LaunchCluster<Cfg, C>, &LaunchDirect<Cfg, 1>, &LaunchUpsweep<Cfg>, nullptr};
+}
+template <int T, int I, bool KV, int M, int LB = 4>
+constexpr PassVariant MakeTmaVariant() {
+  using Cfg = TmaPassConfig<T, I, KV, M, LB>;
+  return PassVariant{T, I, M, true, 0, (uint32_t)Cfg::kTile, Cfg::kSmemBytes, &PrepareTma<Cfg>, &LaunchTma<Cfg, 0>,
+                     &LaunchTma<Cfg, 1>, &LaunchUpsweep<Cfg>, nullptr};
 }
 
+// Direct-load variants (one tile per CTA).  Defaults (measured on B200, profiles/):
+//   onesweep, keys and pairs      index 0  384 x 16, 3 CTAs/SM
+//   reduce-then-scan, keys        index 1  256 x 16, 5 CTAs/SM   (no look-back state in registers)
+//   reduce-then-scan, pairs       index 0
+// The rest are kept selectable for A/B runs (VrdxCudaSorterOptions::reserved / VRDX_*_VARIANT).
 static const PassVariant kKeysVariants[] = {
-    MakeVariant<384, 16, false, 3>(), MakeVariant<256, 16, false, 4>(), MakeVariant<512, 16, false, 2>(),
-    MakeVariant<320, 16, false, 3>(), MakeVariant<512, 12, false, 2>(), MakeVariant<1024, 8, false, 1>(),
-    MakeVariant<512, 8, false, 3>(), MakeVariant<768, 12, false, 1>(),
+    MakeVariant<384, 16, false, 3>(),           MakeVariant<256, 16, false, 5>(),
+    MakeVariant<512, 16, false, 2>(),           MakeVariant<256, 16, false, 4>(),
+    MakeVariant<384, 12, false, 4>(),           MakeVariant<256, 12, false, 6>(),
+    MakeClusterVariant<384, 16, false, 3, 4>(), MakeClusterVariant<384, 16, false, 3, 8>(),
 };
 static const PassVariant kPairVariants[] = {
-    MakeVariant<384, 16, true, 3>(), MakeVariant<256, 16, true, 4>(), MakeVariant<512, 16, true, 2>(),
-    MakeVariant<320, 16, true, 3>(), MakeVariant<512, 12, true, 2>(), MakeVariant<1024, 8, true, 1>(),
-    MakeVariant<512, 8, true, 3>(), MakeVariant<768, 12, true, 1>(),
+    MakeVariant<384, 16, true, 3>(),            MakeVariant<256, 16, true, 5>(),
+    MakeVariant<512, 16, true, 2>(),            MakeVariant<256, 16, true, 4>(),
+    MakeVariant<384, 12, true, 4>(),            MakeVariant<256, 12, true, 6>(),
+    MakeClusterVariant<384, 16, true, 3, 4>(),  MakeClusterVariant<384, 16, true, 3, 8>(),
+};
+constexpr int kDefaultKeysRtsVariant = 1;
+constexpr int kDefaultPairRtsVariant = 0;
+// Persistent TMA-staged variants (selected only with VRDX_CUDA_TILE_LOAD_TMA; measured slower than
+// the direct kernels on B200).
+static const PassVariant kKeysTmaVariants[] = {
+    MakeTmaVariant<256, 16, false, 4>(), MakeTmaVariant<384, 16, false, 3>(), MakeTmaVariant<512, 16, false, 2>(),
+};
+static const PassVariant kPairTmaVariants[] = {
+    MakeTmaVariant<384, 20, true, 2>(), MakeTmaVariant<384, 16, true, 2>(), MakeTmaVariant<512, 16, true, 2>(),
 };
 constexpr int kNumKeysVariants = sizeof(kKeysVariants) / sizeof(kKeysVariants[0]);
 constexpr int kNumPairVariants = sizeof(kPairVariants) / sizeof(kPairVariants[0]);
+constexpr int kNumKeysTmaVariants = sizeof(kKeysTmaVariants) / sizeof(kKeysTmaVariants[0]);
+constexpr int kNumPairTmaVariants = sizeof(kPairTmaVariants) / sizeof(kPairTmaVariants[0]);
 // Smallest tile of any compiled variant: sizes the look-back buffers whichever variant runs.
-constexpr uint32_t kMinTile = 4096;
+constexpr uint32_t kMinTile = 3072;  // 256 x 12
+// AUTO: reduce-then-scan at and above this count, onesweep (fewer launches) below it.
+constexpr uint32_t kAutoRtsThreshold = 3u << 23;  // measured crossover between 2^24 and 2^25 (profiles/r01_sweep_n.txt)
 
 struct VrdxSorter_T {
   int device = 0;
@@ -76,8 +172,10 @@ struct VrdxSorter_T {
   int cc_major = 0, cc_minor = 0;
   VrdxCudaAlgorithm algorithm = VRDX_CUDA_ALGORITHM_AUTO;
   VrdxCudaTileLoad tile_load = VRDX_CUDA_TILE_LOAD_AUTO;
-  int keys_variant = 0;
-  int pair_variant = 0;
+  int keys_variant = 0, pair_variant = 0;          // direct-load kernels, onesweep
+  int keys_rts_variant = kDefaultKeysRtsVariant, pair_rts_variant = kDefaultPairRtsVariant;  // reduce-then-scan
+  int keys_tma_variant = 0, pair_tma_variant = 0;  // persistent TMA kernels
+  int keys_ctas = 1, pair_ctas = 1, keys_tma_ctas = 1, pair_tma_ctas = 1;  // co-resident CTAs per SM
   // The only mutable words: a sticky error and a launch counter (diagnostics, not sort state).
   std::atomic<int> last_error{0};
   std::atomic<uint32_t> last_launches{0};
@@ -163,13 +261,10 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
     sorter->last_launches.store(0);
     return;
   }
-  if ((uint64_t)n_or_max >= kMaxOnesweepCount) {
-    // 30-bit look-back cells; larger counts need the reduce-then-scan path (not built yet).
-    NoteError(sorter, cudaErrorNotSupported);
-    for (uint32_t i = 1; i < 15; ++i) Stamp(sorter, stream, queryPool, query + i);
-    sorter->last_launches.store(0);
-    return;
-  }
+  // 30-bit look-back cells: counts of 2^30 and above take the reduce-then-scan path (32-bit counts).
+  const bool use_rts = sorter->algorithm == VRDX_CUDA_ALGORITHM_REDUCE_THEN_SCAN ||
+                       (uint64_t)n_or_max >= kMaxOnesweepCount ||
+                       (sorter->algorithm == VRDX_CUDA_ALGORITHM_AUTO && n_or_max >= kAutoRtsThreshold);
 
   const StorageLayout lay = ComputeLayout(n_or_max, kMinTile);
   StorageHeader* hdr = reinterpret_cast<StorageHeader*>(storage + lay.header_offset);
@@ -178,24 +273,37 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
   uint32_t* keys_alt = reinterpret_cast<uint32_t*>(storage + lay.keys_alt_offset);
   uint32_t* vals_alt = reinterpret_cast<uint32_t*>(storage + lay.values_alt_offset);
 
-  const PassVariant& variant = kv ? kPairVariants[sorter->pair_variant] : kKeysVariants[sorter->keys_variant];
+  // TMA staging needs 16-byte aligned sources in both ping-pong directions.
+  auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  const bool can_tma = aligned16(keys) && aligned16(storage) && (!kv || aligned16(values));
+  const bool use_tma = sorter->tile_load == VRDX_CUDA_TILE_LOAD_TMA && can_tma;
+  const PassVariant& variant =
+      use_tma ? (kv ? kPairTmaVariants[sorter->pair_tma_variant] : kKeysTmaVariants[sorter->keys_tma_variant])
+              : use_rts ? (kv ? kPairVariants[sorter->pair_rts_variant] : kKeysVariants[sorter->keys_rts_variant])
+                        : (kv ? kPairVariants[sorter->pair_variant] : kKeysVariants[sorter->keys_variant]);
   const uint32_t tiles = (uint32_t)CeilDiv(n_or_max, variant.tile);
+  uint32_t pass_grid = tiles;
+  if (!use_rts && !use_tma && variant.cluster > 1)  // whole clusters; CTAs past the count only serve their digit slice
+    pass_grid = (uint32_t)CeilDiv(tiles, (uint64_t)variant.cluster) * (uint32_t)variant.cluster;
+  if (use_tma) {  // persistent: one wave of co-resident CTAs
+    const uint32_t wave = (uint32_t)sorter->sm_count * (uint32_t)(kv ? sorter->pair_tma_ctas : sorter->keys_tma_ctas);
+    pass_grid = tiles < wave ? tiles : wave;
+  }
 
-  // Reset per-sort state inside the stream (reference: vkCmdFillBuffer of the global
-  // histogram, h.in:382): header (histograms, tickets) + the pass-0 look-back cells.
-  NoteError(sorter, cudaMemsetAsync(storage, 0,
-                                    lay.status_a_offset + (uint64_t)tiles * kRadix * sizeof(uint32_t),
-                                    stream));
-  ++launches;
-
-  {
+  if (!use_rts) {
+    // Reset per-sort state inside the stream (reference: vkCmdFillBuffer of the global
+    // histogram, h.in:382): header (histograms, tickets) + the pass-0 look-back cells.
+    NoteError(sorter, cudaMemsetAsync(storage, 0,
+                                      lay.status_a_offset + (uint64_t)tiles * kRadix * sizeof(uint32_t),
+                                      stream));
+    ++launches;
     uint64_t chunks = CeilDiv(n_or_max, (uint64_t)kHistChunk);
     uint64_t cap = (uint64_t)sorter->sm_count * 4;
     uint32_t grid = (uint32_t)(chunks < cap ? (chunks ? chunks : 1) : cap);
     HistogramKernel<<<grid, kHistThreads, 0, stream>>>(keys, indirect, n_or_max, hdr);
     NoteError(sorter, cudaGetLastError());
     ++launches;
-  }
+  }  // reduce-then-scan keeps no state across passes: every table it reads is written first
   Stamp(sorter, stream, queryPool, query + 1);
 
   for (uint32_t pass = 0; pass < (uint32_t)kPasses; ++pass) {
@@ -212,10 +320,30 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
     args.vals_in = kv ? ((pass & 1) ? vals_alt : values) : nullptr;
     args.vals_out = kv ? ((pass & 1) ? values : vals_alt) : nullptr;
 
+    if (use_rts) {
+      // the reference's three stages: status A = [tile][256] histograms -> exclusive prefixes,
+      // status B = spine chunk sums; timestamps fall exactly where the reference puts them
+      args.status = status[0];
+      args.status_next = nullptr;
+      const uint32_t chunks = (uint32_t)CeilDiv(tiles, (uint64_t)kSpineChunk);
+      NoteError(sorter, variant.launch_upsweep(stream, tiles, args));
+      Stamp(sorter, stream, queryPool, query + 2 + 3 * pass + 0);
+      SpineReduceKernel<<<chunks, kRadix, 0, stream>>>(indirect, n_or_max, variant.tile, status[0], status[1]);
+      SpineScanKernel<<<1, kRadix, 0, stream>>>(indirect, n_or_max, variant.tile, pass, status[1], hdr);
+      SpineApplyKernel<<<chunks, kRadix, 0, stream>>>(indirect, n_or_max, variant.tile, status[0], status[1]);
+      NoteError(sorter, cudaGetLastError());
+      Stamp(sorter, stream, queryPool, query + 2 + 3 * pass + 1);
+      NoteError(sorter, variant.launch_downsweep(stream, use_tma ? pass_grid : tiles, args));
+      launches += 5;
+      Stamp(sorter, stream, queryPool, query + 2 + 3 * pass + 2);
+      continue;
+    }
     // One fused kernel per pass: the reference's upsweep and spine slots collapse onto its start.
     Stamp(sorter, stream, queryPool, query + 2 + 3 * pass + 0);
     Stamp(sorter, stream, queryPool, query + 2 + 3 * pass + 1);
-    NoteError(sorter, variant.launch(stream, tiles, args));
+    static const bool inorder = getenv("VRDX_TILE_ORDER") && atoi(getenv("VRDX_TILE_ORDER")) == 1;
+    NoteError(sorter, (inorder && variant.launch_inorder) ? variant.launch_inorder(stream, pass_grid, args)
+                                                          : variant.launch(stream, pass_grid, args));
     ++launches;
     Stamp(sorter, stream, queryPool, query + 2 + 3 * pass + 2);
   }
@@ -247,21 +375,45 @@ VkResult vrdxCudaCreateSorter(const VrdxSorterCreateInfo* pCreateInfo,
   if (prop.major != 10) return VK_ERROR_FEATURE_NOT_PRESENT;  // kernels are built for sm_100a only
 
   DeviceGuard guard(dev);
-  int keys_variant = 0, pair_variant = 0;
+  int keys_variant = 0, pair_variant = 0, keys_tma_variant = 0, pair_tma_variant = 0;
+  VrdxCudaTileLoad tile_load = VRDX_CUDA_TILE_LOAD_AUTO;
   if (const char* e = getenv("VRDX_KEYS_VARIANT")) keys_variant = atoi(e);
   if (const char* e = getenv("VRDX_KV_VARIANT")) pair_variant = atoi(e);
+  int keys_rts_variant = kDefaultKeysRtsVariant, pair_rts_variant = kDefaultPairRtsVariant;
+  if (const char* e = getenv("VRDX_KEYS_RTS_VARIANT")) keys_rts_variant = atoi(e);
+  if (const char* e = getenv("VRDX_KV_RTS_VARIANT")) pair_rts_variant = atoi(e);
+  if (const char* e = getenv("VRDX_KEYS_TMA_VARIANT")) keys_tma_variant = atoi(e);
+  if (const char* e = getenv("VRDX_KV_TMA_VARIANT")) pair_tma_variant = atoi(e);
+  if (const char* e = getenv("VRDX_TILE_LOAD")) tile_load = (VrdxCudaTileLoad)atoi(e);
   if (pOptions && pOptions->structSize >= sizeof(VrdxCudaSorterOptions)) {
+    if (pOptions->tileLoad != VRDX_CUDA_TILE_LOAD_AUTO) tile_load = pOptions->tileLoad;
     if (pOptions->reserved[0]) keys_variant = (int)pOptions->reserved[0] - 1;
     if (pOptions->reserved[1]) pair_variant = (int)pOptions->reserved[1] - 1;
+    if (pOptions->reserved[2]) keys_tma_variant = (int)pOptions->reserved[2] - 1;
+    if (pOptions->reserved[3]) pair_tma_variant = (int)pOptions->reserved[3] - 1;
+    if (pOptions->reserved[4]) keys_rts_variant = pair_rts_variant = (int)pOptions->reserved[4] - 1;
   }
-  if (keys_variant < 0 || keys_variant >= kNumKeysVariants || pair_variant < 0 || pair_variant >= kNumPairVariants)
+  if (keys_variant < 0 || keys_variant >= kNumKeysVariants || pair_variant < 0 || pair_variant >= kNumPairVariants ||
+      keys_rts_variant < 0 || keys_rts_variant >= kNumKeysVariants || pair_rts_variant < 0 ||
+      pair_rts_variant >= kNumPairVariants || kKeysVariants[keys_rts_variant].cluster > 1 ||
+      kPairVariants[pair_rts_variant].cluster > 1 ||
+      keys_tma_variant < 0 || keys_tma_variant >= kNumKeysTmaVariants || pair_tma_variant < 0 ||
+      pair_tma_variant >= kNumPairTmaVariants)
     return VK_ERROR_INITIALIZATION_FAILED;
-  // "Pipeline creation": opt the pass kernels into their shared-memory footprint.
-  if (kKeysVariants[keys_variant].prepare() != cudaSuccess || kPairVariants[pair_variant].prepare() != cudaSuccess) {
+  // "Pipeline creation": opt the pass kernels into their shared-memory footprint and ask how many
+  // CTAs of each are co-resident per SM (the persistent kernels launch exactly one such wave).
+  int keys_ctas = 1, pair_ctas = 1, keys_tma_ctas = 1, pair_tma_ctas = 1;
+  int unused = 0;
+  if (kKeysVariants[keys_rts_variant].prepare(&unused) != cudaSuccess ||
+      kPairVariants[pair_rts_variant].prepare(&unused) != cudaSuccess ||
+      kKeysVariants[keys_variant].prepare(&keys_ctas) != cudaSuccess ||
+      kPairVariants[pair_variant].prepare(&pair_ctas) != cudaSuccess ||
+      kKeysTmaVariants[keys_tma_variant].prepare(&keys_tma_ctas) != cudaSuccess ||
+      kPairTmaVariants[pair_tma_variant].prepare(&pair_tma_ctas) != cudaSuccess || keys_tma_ctas < 1 ||
+      pair_tma_ctas < 1) {
     cudaGetLastError();
     return VK_ERROR_INITIALIZATION_FAILED;
   }
-
   VrdxSorter_T* s = new (std::nothrow) VrdxSorter_T();
   if (!s) return VK_ERROR_OUT_OF_HOST_MEMORY;
   s->device = dev;
@@ -270,10 +422,19 @@ VkResult vrdxCudaCreateSorter(const VrdxSorterCreateInfo* pCreateInfo,
   s->cc_minor = prop.minor;
   s->keys_variant = keys_variant;
   s->pair_variant = pair_variant;
-  if (pOptions && pOptions->structSize >= sizeof(VrdxCudaSorterOptions)) {
+  s->keys_rts_variant = keys_rts_variant;
+  s->pair_rts_variant = pair_rts_variant;
+  s->keys_tma_variant = keys_tma_variant;
+  s->pair_tma_variant = pair_tma_variant;
+  s->keys_ctas = keys_ctas;
+  s->pair_ctas = pair_ctas;
+  s->keys_tma_ctas = keys_tma_ctas;
+  s->pair_tma_ctas = pair_tma_ctas;
+  s->tile_load = tile_load;
+  if (const char* e = getenv("VRDX_ALGORITHM")) s->algorithm = (VrdxCudaAlgorithm)atoi(e);
+  if (pOptions && pOptions->structSize >= sizeof(VrdxCudaSorterOptions) &&
+      pOptions->algorithm != VRDX_CUDA_ALGORITHM_AUTO)
     s->algorithm = pOptions->algorithm;
-    s->tile_load = pOptions->tileLoad;
-  }
   *pSorter = s;
   return VK_SUCCESS;
 }
@@ -484,8 +645,9 @@ void vrdxCudaGetSorterProperties(VrdxSorter sorter, VrdxCudaSorterProperties* p)
   p->smCount = sorter->sm_count;
   p->ccMajor = sorter->cc_major;
   p->ccMinor = sorter->cc_minor;
-  p->keysTileSize = kKeysVariants[sorter->keys_variant].tile;
-  p->keyValueTileSize = kPairVariants[sorter->pair_variant].tile;
+  const bool tma = sorter->tile_load == VRDX_CUDA_TILE_LOAD_TMA;
+  p->keysTileSize = tma ? kKeysTmaVariants[sorter->keys_tma_variant].tile : kKeysVariants[sorter->keys_variant].tile;
+  p->keyValueTileSize = tma ? kPairTmaVariants[sorter->pair_tma_variant].tile : kPairVariants[sorter->pair_variant].tile;
   p->offsetAlignment = kOffsetAlignment;
   p->maxOnesweepCount = (uint32_t)kMaxOnesweepCount;
 }

@@ -33,8 +33,13 @@ struct alignas(16) StorageHeader {
 };
 static_assert(sizeof(StorageHeader) % 16 == 0, "header must keep 16-byte alignment");
 
-inline constexpr uint64_t AlignUp(uint64_t a, uint64_t b) { return (a + b - 1) / b * b; }
-inline constexpr uint64_t CeilDiv(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+#if defined(__CUDACC__)
+#define VRDX_HD __host__ __device__
+#else
+#define VRDX_HD
+#endif
+VRDX_HD inline constexpr uint64_t AlignUp(uint64_t a, uint64_t b) { return (a + b - 1) / b * b; }
+VRDX_HD inline constexpr uint64_t CeilDiv(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 
 struct StorageLayout {
   uint64_t header_offset;

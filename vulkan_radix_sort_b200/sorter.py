@@ -25,14 +25,14 @@ class Sorter:
     """One ``VrdxSorter`` plus a grow-only storage buffer (the caller-owned scratch)."""
 
     def __init__(self, device: int | torch.device = 0, algorithm: int = api.VRDX_CUDA_ALGORITHM_AUTO,
-                 tile_load: int = api.VRDX_CUDA_TILE_LOAD_AUTO):
+                 tile_load: int = api.VRDX_CUDA_TILE_LOAD_AUTO, reserved=None):
         if not torch.cuda.is_available():
             raise RuntimeError("vulkan_radix_sort_b200 needs a CUDA device; there is no CPU fallback")
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         ordinal = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.device = torch.device("cuda", ordinal)
         info = api.VrdxSorterCreateInfo(api.cuda_device(ordinal), api.cuda_device(ordinal), None)
-        res, handle = api.vrdxCudaCreateSorter(info, algorithm, tile_load)
+        res, handle = api.vrdxCudaCreateSorter(info, algorithm, tile_load, reserved)
         if res != api.VK_SUCCESS:
             raise RuntimeError(f"vrdxCreateSorter failed with VkResult {res}")
         self.handle = handle
