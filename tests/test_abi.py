@@ -29,7 +29,8 @@ def _declared_functions(header):
 
 
 def test_library_exports_every_declared_symbol(lib):
-    declared = _declared_functions("vk_radix_sort.h") | _declared_functions("vrdx_cuda.h")
+    declared = (_declared_functions("vk_radix_sort.h") | _declared_functions("vrdx_cuda.h")
+                | _declared_functions("vrdx_dist.h"))
     assert {"vrdxCreateSorter", "vrdxDestroySorter", "vrdxGetSorterStorageRequirements",
             "vrdxGetSorterKeyValueStorageRequirements", "vrdxCmdSort", "vrdxCmdSortIndirect",
             "vrdxCmdSortKeyValue", "vrdxCmdSortKeyValueIndirect"} <= declared

@@ -1,0 +1,109 @@
+"""GPU tests of the multi-GPU building blocks (single GPU) and, when at least two GPUs are visible,
+of the whole distributed sort over NCCL."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a):
+    return torch.from_numpy(a.view(np.int32)).cuda()
+
+
+@pytest.fixture(scope="module")
+def backends():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from dist_numpy_backend import NumpyBackend
+    from vulkan_radix_sort_b200.dist import CudaBackend
+    b = CudaBackend(0)
+    yield b, NumpyBackend()
+    b.close()
+
+
+@pytest.mark.parametrize("dist_name", ["uniform", "bits8", "all_ones", "skewed"])
+def test_prefix_histogram_matches_numpy(backends, dist_name):
+    from vulkan_radix_sort_b200.datagen import make_keys
+    cuda_b, np_b = backends
+    for n in (1, 4099, 1000003):
+        k = make_keys(dist_name, n, seed=3)
+        kt = torch.from_numpy(k.view(np.int32).copy())
+        for shift, prefixes in ((24, [0]), (16, [int(k[0]) >> 24, 0xFF, 0]), (8, [int(k[n // 2]) >> 16, 1]),
+                                (0, [int(k[-1]) >> 8, int(k[0]) >> 8, 0xFFFFFF])):
+            p = torch.tensor(prefixes, dtype=torch.int64)
+            want = np_b.prefix_histogram(kt, n, shift, p)
+            got = cuda_b.prefix_histogram(_dev(k), n, shift, p.cuda()).cpu()
+            assert torch.equal(got, want), (dist_name, n, shift)
+
+
+@pytest.mark.parametrize("dist_name", ["uniform", "bits4", "all_zero", "sentinel_mix"])
+def test_partition_groups_by_class(backends, dist_name):
+    from vulkan_radix_sort_b200.datagen import make_keys
+    cuda_b, _ = backends
+    for n, splitters in ((5, []), (4096, [7]), (100003, [3, 0x40000000, 0xFFFFFFFF]),
+                         (1 << 20, [0, 1, 2, 0x7FFFFFFF, 0x80000000, 0xC0000000, 0xFFFFFFFE])):
+        k = make_keys(dist_name, n, seed=5)
+        u = np.array(splitters, dtype=np.uint64)
+        k64 = k.astype(np.uint64)
+        cls = (2 * (k64[:, None] > u[None, :]).sum(axis=1) + (k64[:, None] == u[None, :]).any(axis=1)) if u.size \
+            else np.zeros(n, dtype=np.int64)
+        sizes = np.bincount(cls, minlength=2 * len(splitters) + 1)
+        starts = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+        out = torch.zeros(n, dtype=torch.int32, device="cuda")
+        cuda_b.partition(_dev(k), n, torch.tensor(splitters, dtype=torch.int64, device="cuda"),
+                         torch.tensor(starts, dtype=torch.int64, device="cuda"), out)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy().view(np.uint32)
+        for c, (a, sz) in enumerate(zip(starts, sizes)):           # same multiset per class, any order inside
+            assert np.array_equal(np.sort(got[a:a + sz]), np.sort(k[cls == c])), (dist_name, n, c)
+
+
+def _nccl_worker(rank, world, port, dist_name, n, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from vulkan_radix_sort_b200.datagen import make_keys
+        from vulkan_radix_sort_b200.dist import CudaBackend, distributed_sort
+        k = make_keys(dist_name, n + 13 * rank, seed=1 + rank)
+        backend = CudaBackend(rank)
+        recv, cnt, plan = distributed_sort(backend, torch.from_numpy(k.view(np.int32).copy()).cuda(), k.size)
+        torch.cuda.synchronize()
+        q.put((rank, k, recv[:cnt].cpu().numpy().view(np.uint32).copy(), plan.targets))
+        backend.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dist_name", ["uniform", "all_zero", "skewed"])
+def test_distributed_sort_over_nccl(oracle, dist_name):
+    world = torch.cuda.device_count()
+    if world < 2:
+        pytest.skip("needs at least two GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, dist_name, 3_000_017, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted([q.get(timeout=300) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    union = np.concatenate([r[1] for r in results])
+    assert np.array_equal(np.concatenate([r[2] for r in results]), oracle.sort_keys(union))
+    for rank, _, out, targets in results:
+        assert out.size == targets[rank + 1] - targets[rank]

@@ -82,6 +82,11 @@ _SIGNATURES = {
     "vrdxCudaImportedMemoryBuffer": (c_void_p, [c_void_p, c_uint64]),
     "vrdxCudaReleaseImportedMemory": (None, [c_void_p]),
     "vrdxCudaGetSorterProperties": (None, [c_void_p, POINTER(VrdxCudaSorterProperties)]),
+    # include/vrdx_dist.h
+    "vrdxDistCmdPrefixHistogram": (None, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_uint32, c_uint32,
+                                          c_void_p, c_uint64, c_void_p, c_uint64]),
+    "vrdxDistCmdPartition": (None, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_uint32, c_void_p, c_uint64,
+                                    c_void_p, c_uint64, c_void_p, c_uint64]),
 }
 
 REFERENCE_ENTRY_POINTS = tuple(list(_SIGNATURES)[:8])  # the eight functions of src/vk_radix_sort.h.in:24-81

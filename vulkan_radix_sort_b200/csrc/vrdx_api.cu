@@ -20,6 +20,8 @@
 #define VRDX_FORCE_VK_SHIM 1
 #include "vk_radix_sort.h"
 #include "vrdx_cuda.h"
+#include "vrdx_dist.h"
+#include "vrdx_dist_kernels.cuh"
 #include "vrdx_kernels.cuh"
 #include "vrdx_layout.h"
 
@@ -650,6 +652,59 @@ void vrdxCudaGetSorterProperties(VrdxSorter sorter, VrdxCudaSorterProperties* p)
   p->keyValueTileSize = tma ? kPairTmaVariants[sorter->pair_tma_variant].tile : kPairVariants[sorter->pair_variant].tile;
   p->offsetAlignment = kOffsetAlignment;
   p->maxOnesweepCount = (uint32_t)kMaxOnesweepCount;
+}
+
+// ---------------------------------------------------------------------------- multi-GPU building blocks
+
+void vrdxDistCmdPrefixHistogram(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t elementCount,
+                                VkBuffer keysBuffer, VkDeviceSize keysOffset, uint32_t shift,
+                                uint32_t prefixCount, VkBuffer prefixesBuffer, VkDeviceSize prefixesOffset,
+                                VkBuffer histogramBuffer, VkDeviceSize histogramOffset) {
+  if (!sorter) return;
+  if (!keysBuffer || !histogramBuffer || prefixCount == 0 || prefixCount > (uint32_t)kDistMaxSplitters ||
+      shift > 24 || (shift & 7u) || (!prefixesBuffer && shift < 24)) {
+    NoteError(sorter, cudaErrorInvalidValue);
+    return;
+  }
+  if (elementCount == 0) return;
+  DeviceGuard guard(sorter->device);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(commandBuffer);
+  const uint32_t* keys = reinterpret_cast<const uint32_t*>(reinterpret_cast<char*>(keysBuffer) + keysOffset);
+  const uint32_t* prefixes =
+      prefixesBuffer ? reinterpret_cast<const uint32_t*>(reinterpret_cast<char*>(prefixesBuffer) + prefixesOffset)
+                     : reinterpret_cast<const uint32_t*>(keys);  // never read when shift == 24
+  uint32_t* hist = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(histogramBuffer) + histogramOffset);
+  const uint64_t vec_blocks = CeilDiv((uint64_t)elementCount / 4 + 1, (uint64_t)kDistHistThreads);
+  const uint64_t cap = (uint64_t)sorter->sm_count * 4;
+  const uint32_t grid = (uint32_t)(vec_blocks < cap ? vec_blocks : cap);
+  DistPrefixHistogramKernel<<<grid, kDistHistThreads, prefixCount * kRadix * sizeof(uint32_t), stream>>>(
+      keys, elementCount, shift, prefixCount, prefixes, hist);
+  NoteError(sorter, cudaGetLastError());
+}
+
+void vrdxDistCmdPartition(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t elementCount,
+                          VkBuffer keysBuffer, VkDeviceSize keysOffset, uint32_t splitterCount,
+                          VkBuffer splittersBuffer, VkDeviceSize splittersOffset, VkBuffer cursorsBuffer,
+                          VkDeviceSize cursorsOffset, VkBuffer outBuffer, VkDeviceSize outOffset) {
+  if (!sorter) return;
+  if (!keysBuffer || !outBuffer || !cursorsBuffer || splitterCount > (uint32_t)kDistMaxSplitters ||
+      (splitterCount && !splittersBuffer)) {
+    NoteError(sorter, cudaErrorInvalidValue);
+    return;
+  }
+  if (elementCount == 0) return;
+  DeviceGuard guard(sorter->device);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(commandBuffer);
+  const uint32_t* keys = reinterpret_cast<const uint32_t*>(reinterpret_cast<char*>(keysBuffer) + keysOffset);
+  const uint32_t* splitters =
+      splittersBuffer ? reinterpret_cast<const uint32_t*>(reinterpret_cast<char*>(splittersBuffer) + splittersOffset)
+                      : keys;  // never read when splitterCount == 0
+  uint32_t* cursors = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(cursorsBuffer) + cursorsOffset);
+  uint32_t* out = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(outBuffer) + outOffset);
+  const uint32_t grid = (uint32_t)CeilDiv((uint64_t)elementCount, (uint64_t)kDistPartTile);
+  DistPartitionKernel<<<grid, kDistPartThreads, 0, stream>>>(keys, elementCount, splitterCount, splitters,
+                                                             cursors, out);
+  NoteError(sorter, cudaGetLastError());
 }
 
 }  // extern "C"

@@ -1,0 +1,166 @@
+// vrdx_dist_kernels.cuh — kernels of the multi-GPU sort: splitter-search histograms and the
+// class multi-split that precedes the NVLink exchange.  No reference counterpart (the reference
+// is single-device); see include/vrdx_dist.h for the contracts.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vrdx_kernels.cuh"
+
+namespace vrdx {
+
+constexpr int kDistMaxSplitters = 15;
+constexpr int kDistMaxClasses = 2 * kDistMaxSplitters + 1;
+
+struct DistPrefixes {
+  uint32_t count;
+  uint32_t shift;
+};
+
+// ---- splitter search: per-prefix 256-bin histograms -----------------------------------------
+// Algorithmic traffic 4 B/key.  Grid-stride, 128-bit loads, shared-memory histograms
+// (prefixCount x 256 bins), one global atomic per non-empty bin at the end.
+constexpr int kDistHistThreads = 512;
+
+__global__ void __launch_bounds__(kDistHistThreads)
+DistPrefixHistogramKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t shift, uint32_t prefix_count,
+                          const uint32_t* __restrict__ prefixes, uint32_t* __restrict__ hist) {
+  extern __shared__ uint32_t sh[];  // [prefix_count][256]
+  __shared__ uint32_t s_prefix[kDistMaxSplitters];
+  const int tid = threadIdx.x;
+  for (uint32_t i = tid; i < prefix_count * kRadix; i += kDistHistThreads) sh[i] = 0;
+  if (tid < (int)prefix_count) s_prefix[tid] = prefixes[tid];
+  __syncthreads();
+  const bool top = shift >= 24;  // no bits above the digit: every key matches
+  auto count_key = [&](uint32_t k) {
+    const uint32_t d = (k >> shift) & 0xFFu;
+    const uint32_t hi = top ? 0u : (k >> (shift + 8));
+    for (uint32_t j = 0; j < prefix_count; ++j)
+      if (top || hi == s_prefix[j]) atomicAdd(&sh[j * kRadix + d], 1u);
+  };
+  const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(keys) >> 2) & 3u);
+  uint32_t head = mis ? 4u - mis : 0u;
+  if (head > n) head = n;
+  const uint4* __restrict__ body = reinterpret_cast<const uint4*>(keys + head);
+  const uint64_t nvec = (uint64_t)(n - head) >> 2;
+  const uint32_t tail_start = head + (uint32_t)(nvec << 2);
+  for (uint64_t v = (uint64_t)blockIdx.x * kDistHistThreads + tid; v < nvec;
+       v += (uint64_t)gridDim.x * kDistHistThreads) {
+    const uint4 q = __ldcs(body + v);
+    count_key(q.x); count_key(q.y); count_key(q.z); count_key(q.w);
+  }
+  if (blockIdx.x == 0) {
+    if ((uint32_t)tid < head) count_key(keys[tid]);
+    const uint32_t t = tail_start + tid;
+    if (tid < 4 && t < n) count_key(keys[t]);
+  }
+  __syncthreads();
+  for (uint32_t i = tid; i < prefix_count * kRadix; i += kDistHistThreads) {
+    const uint32_t c = sh[i];
+    if (c) atomicAdd(hist + i, c);
+  }
+}
+
+// ---- class multi-split ------------------------------------------------------------------------
+// One tile per CTA; a class is a 5-bit label, so peers inside a warp come from a 5-round ballot
+// loop (cheap here: 5 instead of 8 rounds, and the kernel runs once per sort).  Tile-local reorder
+// through shared memory makes the global writes run-wise coalesced; each tile reserves its output
+// range per class with one global atomic (order between tiles is irrelevant for keys-only).
+constexpr int kDistPartThreads = 256;
+constexpr int kDistPartItems = 16;
+constexpr int kDistPartTile = kDistPartThreads * kDistPartItems;
+constexpr int kDistClassSlots = 32;  // classes padded to a power of two
+
+__global__ void __launch_bounds__(kDistPartThreads)
+DistPartitionKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t splitter_count,
+                    const uint32_t* __restrict__ splitters, uint32_t* __restrict__ cursors,
+                    uint32_t* __restrict__ out) {
+  constexpr int kWarps = kDistPartThreads / 32;
+  __shared__ uint32_t s_u[kDistMaxSplitters];
+  __shared__ uint32_t s_cnt[kWarps][kDistClassSlots];  // per-warp class counts, later slot bases
+  __shared__ uint32_t s_base[kDistClassSlots];         // tile-local first slot of each class
+  __shared__ uint32_t s_gbase[kDistClassSlots];        // global slot of tile-local slot 0, per class
+  __shared__ uint32_t s_keys[kDistPartTile];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t tile_start = (uint64_t)blockIdx.x * kDistPartTile;
+  if (tile_start >= n) return;
+  const uint32_t remaining = (uint32_t)(n - tile_start);
+  const uint32_t tile_count = remaining < (uint32_t)kDistPartTile ? remaining : (uint32_t)kDistPartTile;
+  if (tid < (int)splitter_count) s_u[tid] = splitters[tid];
+  if (lane < kDistClassSlots) s_cnt[warp][lane] = 0;
+  __syncthreads();
+
+  const uint32_t lt = LaneMaskLt();
+  const uint32_t woff = warp * 32 * kDistPartItems + lane;
+  const uint32_t* kin = keys + tile_start + woff;
+  uint32_t key[kDistPartItems], rank[kDistPartItems];
+  uint8_t cls[kDistPartItems];
+#pragma unroll
+  for (int i = 0; i < kDistPartItems; ++i)
+    key[i] = (woff + 32 * i < tile_count) ? LdStream(kin + 32 * i) : 0xFFFFFFFFu;
+#pragma unroll
+  for (int i = 0; i < kDistPartItems; ++i) {
+    const bool valid = woff + 32 * i < tile_count;
+    uint32_t gt = 0, eq = 0;
+    for (uint32_t j = 0; j < splitter_count; ++j) {
+      gt += key[i] > s_u[j];
+      eq |= key[i] == s_u[j];
+    }
+    // invalid (pad) lanes take the unused top slot so that they rank after every real key
+    const uint32_t c = valid ? 2u * gt + eq : (uint32_t)(kDistClassSlots - 1);
+    cls[i] = (uint8_t)c;
+    uint32_t peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+      const bool bit = (c >> b) & 1u;
+      const uint32_t m = __ballot_sync(0xffffffffu, bit);
+      peers &= bit ? m : ~m;
+    }
+    const uint32_t before = s_cnt[warp][c];
+    const uint32_t below = __popc(peers & lt);
+    __syncwarp();
+    if (below == 0) s_cnt[warp][c] = before + __popc(peers);
+    __syncwarp();
+    rank[i] = before + below;
+  }
+  __syncthreads();
+  if (tid < kDistClassSlots) {  // one thread per class: totals over warps, tile scan, global reservation
+    uint32_t sum = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      const uint32_t c = s_cnt[w][tid];
+      s_cnt[w][tid] = sum;
+      sum += c;
+    }
+    const uint32_t incl = WarpInclusiveScan(sum, lane);
+    const uint32_t excl = incl - sum;
+    s_base[tid] = excl;
+    const bool real = tid < (int)(2 * splitter_count + 1);
+    const uint32_t g = (real && sum) ? atomicAdd(&cursors[tid], sum) : 0u;
+    s_gbase[tid] = g - excl;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kDistPartItems; ++i) {
+    const uint32_t c = cls[i];
+    rank[i] += s_cnt[warp][c] + s_base[c];
+    s_keys[rank[i]] = key[i];
+  }
+  __syncthreads();
+  // real keys occupy tile-local slots [0, tile_count); recompute the class from the key
+#pragma unroll
+  for (int i = 0; i < kDistPartItems; ++i) {
+    const uint32_t slot = i * kDistPartThreads + tid;
+    if (slot < tile_count) {
+      const uint32_t k = s_keys[slot];
+      uint32_t gt = 0, eq = 0;
+      for (uint32_t j = 0; j < splitter_count; ++j) {
+        gt += k > s_u[j];
+        eq |= k == s_u[j];
+      }
+      out[s_gbase[2u * gt + eq] + slot] = k;
+    }
+  }
+}
+
+}  // namespace vrdx

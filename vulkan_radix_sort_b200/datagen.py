@@ -25,7 +25,13 @@ class DataGenerator:
         self._bitgen._legacy_seeding(int(seed) & 0xFFFFFFFF)
 
     def raw(self, n: int) -> np.ndarray:
-        return self._bitgen.random_raw(int(n)).astype(np.uint32)
+        n = int(n)
+        out = np.empty(n, dtype=np.uint32)
+        chunk = 1 << 24  # random_raw yields uint64: bound the transient footprint
+        for a in range(0, n, chunk):
+            b = min(n, a + chunk)
+            out[a:b] = self._bitgen.random_raw(b - a)
+        return out
 
     def generate(self, size: int, bits: int = 32):
         """-> (keys, values), like SortData Generate(size, bits) (bench/data_generator.cc:12-27)."""

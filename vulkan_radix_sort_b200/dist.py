@@ -1,0 +1,216 @@
+"""Multi-GPU keys-only sort: one process per GPU, torch.distributed for the plumbing.
+
+BASELINE.json configs[4] / SURVEY.md §8(e).  The reference is single-device; this layer is new:
+
+  1. exact splitters — a 4-level (8 bits per level) distributed histogram search finds, for every
+     boundary k = 1..G-1, the key value v_k at global rank T_k = k*N/G together with the number of
+     keys below it and equal to it (globally and per rank).  Cost: four 4 B/key reads of the local
+     keys and four tiny all-reduces.  The partition is balanced to +-1 key for ANY input
+     distribution: ties on a splitter value (an all-equal input is one big tie) are split by
+     source rank, which is legal for a keys-only sort because equal keys are indistinguishable;
+  2. local multi-split (vrdxDistCmdPartition) into <= 2G-1 classes (open intervals between
+     splitters and one tie class per distinct splitter value), class-ordered, so the keys bound
+     for each destination rank are ONE contiguous slice of the output;
+  3. all-to-all-v of those slices (NCCL grouped send/recv over NVLink / NVSwitch);
+  4. local LSD sort of what arrived (vrdxCmdSort through the C-ABI).
+
+Afterwards rank r holds the keys of global ranks [T_r, T_{r+1}) in ascending order, so the
+concatenation over ranks is the sorted input — bit-identical to a single-device sort.
+
+The numerical work is behind a small ``Backend`` object: ``CudaBackend`` calls the C-ABI; the
+tests supply a NumPy stand-in so that this host logic runs under gloo on CPU.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+LEVEL_SHIFTS = (24, 16, 8, 0)
+
+
+def _u32_as_i32(t: torch.Tensor) -> torch.Tensor:
+    """int64 tensor of values in [0, 2^32) -> int32 tensor with the same low 32 bits."""
+    t = t.to(torch.int64)
+    return torch.where(t >= (1 << 31), t - (1 << 32), t).to(torch.int32).contiguous()
+
+
+# ------------------------------------------------------------------------------ backends
+
+class CudaBackend:
+    """The product path: every numerical step is a kernel of libvrdx_b200.so."""
+
+    def __init__(self, device: int):
+        from . import api
+        from .sorter import Sorter
+        self.api = api
+        self.sorter = Sorter(device)
+        self.device = self.sorter.device
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def prefix_histogram(self, keys: torch.Tensor, count: int, shift: int, prefixes: torch.Tensor) -> torch.Tensor:
+        """-> int64 [P, 256]: local digit histogram at `shift` of the keys matching each prefix."""
+        p = int(prefixes.numel())
+        hist = torch.zeros(p * 256, dtype=torch.int32, device=self.device)
+        pref32 = _u32_as_i32(prefixes)
+        self.api.load_library().vrdxDistCmdPrefixHistogram(
+            self._stream(), self.sorter.handle, count, keys.data_ptr(), 0, shift, p, pref32.data_ptr(), 0,
+            hist.data_ptr(), 0)
+        self.sorter.check()
+        return (hist.to(torch.int64) & 0xFFFFFFFF).view(p, 256)
+
+    def partition(self, keys: torch.Tensor, count: int, splitters: torch.Tensor, class_starts: torch.Tensor,
+                  out: torch.Tensor) -> None:
+        m = int(splitters.numel())
+        spl = _u32_as_i32(splitters) if m else None
+        cursors = _u32_as_i32(class_starts)
+        self.api.load_library().vrdxDistCmdPartition(
+            self._stream(), self.sorter.handle, count, keys.data_ptr(), 0, m, spl.data_ptr() if m else None, 0,
+            cursors.data_ptr(), 0, out.data_ptr(), 0)
+        self.sorter.check()
+
+    def local_sort(self, keys: torch.Tensor, count: int, storage: torch.Tensor | None = None) -> None:
+        self.sorter.sort(keys, count=count, storage=storage)
+
+    def storage_for(self, max_count: int) -> torch.Tensor:
+        return self.sorter.storage_for(max_count, False)
+
+    def close(self):
+        self.sorter.close()
+
+
+# ------------------------------------------------------------------------------ host logic
+
+@dataclass
+class SplitPlan:
+    """Everything every rank needs to know about the exchange (identical on all ranks)."""
+    total: int                    # N = sum of local counts
+    targets: list                 # T_k, k = 0..G
+    splitters: list               # v_k for k = 1..G-1 (may repeat)
+    distinct: list                # ascending distinct splitter values u_i
+    sizes: list                   # sizes[s][j] = keys rank s sends to rank j
+    class_starts: list            # this rank's first output slot per class (2m+1 entries)
+
+
+def _as_u32_tensor(values, device):
+    return torch.tensor([int(v) for v in values], dtype=torch.int64, device=device)
+
+
+def find_splitters(backend, keys: torch.Tensor, count: int, group=None):
+    """The 4-level search.  Returns per boundary k=1..G-1 (tensors on keys.device, int64):
+    value v_k, global #keys < v_k, global #keys == v_k, local #keys < v_k, local #keys == v_k;
+    plus N and the targets T_k."""
+    world = dist.get_world_size(group)
+    device = keys.device
+    n_local = torch.tensor([count], dtype=torch.int64, device=device)
+    n_total_t = n_local.clone()
+    dist.all_reduce(n_total_t, group=group)
+    total = int(n_total_t.item())
+    targets = [k * total // world for k in range(world + 1)]
+    nb = world - 1
+    if nb == 0 or total == 0:
+        z = torch.zeros(0, dtype=torch.int64, device=device)
+        return z, z, z, z, z, total, targets
+    remaining = torch.tensor(targets[1:world], dtype=torch.int64, device=device)  # rank of the wanted key inside the current bucket
+    prefix = torch.zeros(nb, dtype=torch.int64, device=device)
+    less_g = torch.zeros(nb, dtype=torch.int64, device=device)
+    less_l = torch.zeros(nb, dtype=torch.int64, device=device)
+    eq_g = eq_l = None
+    for level, shift in enumerate(LEVEL_SHIFTS):
+        if level == 0:
+            h_local = backend.prefix_histogram(keys, count, shift, prefix[:1]).expand(nb, 256)
+        else:
+            h_local = backend.prefix_histogram(keys, count, shift, prefix)
+        h_global = h_local.clone().contiguous()
+        dist.all_reduce(h_global, group=group)
+        cum = torch.cumsum(h_global, dim=1)                       # inclusive
+        digit = (cum <= remaining[:, None]).sum(dim=1)            # first digit whose cumulative count exceeds the target rank
+        digit = digit.clamp(max=255)
+        excl_g = torch.where(digit > 0, cum.gather(1, (digit - 1).clamp(min=0)[:, None])[:, 0], torch.zeros_like(remaining))
+        cum_l = torch.cumsum(h_local, dim=1)
+        excl_l = torch.where(digit > 0, cum_l.gather(1, (digit - 1).clamp(min=0)[:, None])[:, 0], torch.zeros_like(remaining))
+        less_g = less_g + excl_g
+        less_l = less_l + excl_l
+        remaining = remaining - excl_g
+        prefix = prefix * 256 + digit
+        eq_g = h_global.gather(1, digit[:, None])[:, 0]
+        eq_l = h_local.gather(1, digit[:, None])[:, 0]
+    return prefix, less_g, eq_g, less_l, eq_l, total, targets
+
+
+def make_plan(backend, keys: torch.Tensor, count: int, group=None) -> SplitPlan:
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    v, less_g, eq_g, less_l, eq_l, total, targets = find_splitters(backend, keys, count, group)
+    nb = world - 1
+    # every rank's local statistics: [count, less_l(1..nb), eq_l(1..nb)]
+    mine = torch.cat([torch.tensor([count], dtype=torch.int64, device=keys.device), less_l, eq_l]).contiguous()
+    everyone = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(everyone, mine, group=group)
+    stats = torch.stack(everyone).cpu().tolist()                 # the one host synchronisation of the plan
+    v_h, less_g_h = v.cpu().tolist(), less_g.cpu().tolist()
+    counts = [int(r[0]) for r in stats]
+    less_l_all = [[int(x) for x in r[1:1 + nb]] for r in stats]
+    eq_l_all = [[int(x) for x in r[1 + nb:1 + 2 * nb]] for r in stats]
+    # local boundary positions a[s][k]: the first a[s][k] keys (in class order) of rank s go to ranks < k
+    sizes = []
+    for s in range(world):
+        a = [0]
+        for k in range(nb):
+            need_left = targets[k + 1] - less_g_h[k]             # ties that must end up left of boundary k+1, globally
+            before = sum(eq_l_all[t][k] for t in range(s))       # ties held by lower ranks go first
+            left = min(max(need_left - before, 0), eq_l_all[s][k])
+            a.append(less_l_all[s][k] + left)
+        a.append(counts[s])
+        for k in range(1, len(a)):                               # duplicates among splitters keep positions monotone
+            a[k] = max(a[k], a[k - 1])
+        sizes.append([a[j + 1] - a[j] for j in range(world)])
+    distinct = sorted(set(int(x) for x in v_h))
+    # class layout of THIS rank: [interior_0][tie_0][interior_1][tie_1]...[interior_m]
+    starts = [0]
+    for u in distinct:
+        k = v_h.index(u)
+        starts.append(less_l_all[rank][k])                       # tie class starts after everything smaller
+        starts.append(less_l_all[rank][k] + eq_l_all[rank][k])   # next interior class
+    class_starts = starts[:2 * len(distinct) + 1]
+    return SplitPlan(total, targets, [int(x) for x in v_h], distinct, sizes, class_starts)
+
+
+def distributed_sort(backend, keys: torch.Tensor, count: int | None = None, group=None, recv: torch.Tensor | None = None,
+                     part: torch.Tensor | None = None, storage: torch.Tensor | None = None, timers=None):
+    """Sort the union of every rank's keys[0:count].  Returns (recv_buffer, recv_count): rank r's
+    slice of the globally sorted sequence (global ranks [T_r, T_{r+1}))."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n = int(keys.numel() if count is None else count)
+    device = keys.device
+
+    def mark(name):
+        if timers is not None:
+            timers.mark(name)
+
+    mark("start")
+    plan = make_plan(backend, keys, n, group)
+    mark("splitters")
+    in_splits = plan.sizes[rank]
+    out_splits = [plan.sizes[s][rank] for s in range(world)]
+    recv_count = sum(out_splits)
+    if part is None:
+        part = torch.empty(max(n, 1), dtype=keys.dtype, device=device)
+    if recv is None or recv.numel() < recv_count:
+        recv = torch.empty(max(recv_count, 1), dtype=keys.dtype, device=device)
+    if n:
+        backend.partition(keys, n, _as_u32_tensor(plan.distinct, device), _as_u32_tensor(plan.class_starts, device), part)
+    mark("partition")
+    if world > 1:
+        dist.all_to_all_single(recv[:recv_count], part[:n], out_splits, in_splits, group=group)
+    else:
+        recv[:recv_count].copy_(part[:n])
+    mark("exchange")
+    if recv_count:
+        backend.local_sort(recv, recv_count, storage)
+    mark("local_sort")
+    return recv, recv_count, plan

@@ -1,0 +1,159 @@
+"""bench.py --gpus N (N > 1): BASELINE.json configs[4] — distributed keys-only sort, 2^29 uniform
+keys per GPU (weak scaling), exact-splitter partition + NCCL all-to-all-v over NVLink + local
+LSD sort.  One process per GPU (launched by torch.distributed.run); rank 0 prints the JSON line.
+Timing: CUDA events on each rank's stream around the whole distributed sort, MAX over ranks."""
+from __future__ import annotations
+
+import json
+import os
+import statistics
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class _Timers:
+    """CUDA-event marks at the stage boundaries of distributed_sort."""
+
+    def __init__(self):
+        self.events = []
+
+    def mark(self, name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.events.append((name, e))
+
+    def stages_ms(self):
+        out = {}
+        for (_, a), (name, b) in zip(self.events, self.events[1:]):
+            out[name] = a.elapsed_time(b)
+        return out
+
+
+def run(args, metric, unit):
+    from bench import ClockSampler, measured_peak_gbs  # the shared helpers live in bench.py
+    from oracle import cpu_oracle
+    from .datagen import DataGenerator
+    from .dist import CudaBackend, distributed_sort
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29511")
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    steps, warmup = args.steps, max(3, args.warmup)
+    n = 1 << args.log2n_per_gpu
+
+    host_keys = DataGenerator(1 + rank).generate(n, 32)[0]      # per-rank seed = 1 + rank
+    pristine = torch.from_numpy(host_keys.view(np.int32)).cuda()
+    keys = torch.empty_like(pristine)
+    backend = CudaBackend(local_rank)
+    cap = n + (n >> 6) + 1024                                    # exact splitters: every rank receives N/G +- 1
+    part = torch.empty(n, dtype=torch.int32, device="cuda")
+    recv = torch.empty(cap, dtype=torch.int32, device="cuda")
+    storage = backend.storage_for(cap)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    times, stage_acc = [], {}
+    recv_count = 0
+    for it in range(warmup + steps):
+        keys.copy_(pristine)
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        tm = _Timers()
+        _, recv_count, plan = distributed_sort(backend, keys, n, recv=recv, part=part, storage=storage, timers=tm)
+        torch.cuda.synchronize()
+        dist.barrier()
+        if it >= warmup:
+            st = tm.stages_ms()
+            ms = torch.tensor([sum(st.values())] + [st[k] for k in ("splitters", "partition", "exchange", "local_sort")],
+                              dtype=torch.float64, device="cuda")
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)           # max over ranks, per stage and in total
+            vals = ms.cpu().tolist()
+            times.append(vals[0])
+            for k, v in zip(("splitters", "partition", "exchange", "local_sort"), vals[1:]):
+                stage_acc.setdefault(k, []).append(v)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- verification (untimed): local order, rank boundaries, global multiset ----------------------
+    out = recv[:recv_count].cpu().numpy().view(np.uint32)
+    ok_sorted = cpu_oracle.is_sorted(out)
+    edge = torch.tensor([int(out[0]) if recv_count else 0, int(out[-1]) if recv_count else 0, recv_count],
+                        dtype=torch.int64, device="cuda")
+    edges = [torch.empty_like(edge) for _ in range(world)]
+    dist.all_gather(edges, edge)
+    edges = [e.cpu().tolist() for e in edges]
+    ok_bounds = all(edges[r][1] <= edges[r + 1][0] for r in range(world - 1) if edges[r][2] and edges[r + 1][2])
+    fp_in = cpu_oracle.multiset_fingerprint(host_keys)
+    fp_out = cpu_oracle.multiset_fingerprint(out)
+    # sums are mod 2^64: carry them as two 32-bit halves so the all-reduce cannot overflow int64
+    def halves(x):
+        return [x & 0xFFFFFFFF, x >> 32]
+    fp = torch.tensor(halves(fp_in[0]) + halves(fp_out[0]) + [recv_count, n], dtype=torch.int64, device="cuda")
+    dist.all_reduce(fp)
+    f = fp.cpu().tolist()
+    sum_in = (f[0] + (f[1] << 32)) & ((1 << 64) - 1)
+    sum_out = (f[2] + (f[3] << 32)) & ((1 << 64) - 1)
+    ok_multiset = (sum_in == sum_out) and (f[4] == f[5])
+    verified = bool(ok_sorted and ok_bounds and ok_multiset)
+
+    # ---- end to end with host buffers (pinned H2D + distributed sort + D2H of the local slice) -------
+    pinned_in = torch.from_numpy(host_keys.view(np.int32)).pin_memory()
+    pinned_out = torch.empty(cap, dtype=torch.int32).pin_memory()
+    e2e_times = []
+    for it in range(1 + 2):
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        keys.copy_(pinned_in, non_blocking=True)
+        _, rc, _ = distributed_sort(backend, keys, n, recv=recv, part=part, storage=storage)
+        pinned_out[:rc].copy_(recv[:rc], non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if it >= 1:
+            e2e_times.append(float(t.item()))
+
+    if rank == 0:
+        ms_per_step = sum(times) / len(times)
+        value = world * n / (ms_per_step * 1e-3) / 1e9
+        e2e_ms = sum(e2e_times) / len(e2e_times)
+        peak, peak_src = measured_peak_gbs()
+        stages = {k: statistics.mean(v) for k, v in stage_acc.items()}
+        sort_ms = stages["local_sort"]
+        launches = backend.sorter.last_launch_count + 4 + 1      # local sort + 4 histogram levels + partition
+        line = {
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"distributed 32-bit keys-only sort, 2^{args.log2n_per_gpu} uniform keys per GPU "
+                                   f"(DataGenerator seed 1+rank), {world} GPUs: exact-splitter MSD partition + NCCL "
+                                   f"all-to-all-v + local LSD sort",
+                       "l2": "per-GPU inputs (2 GiB) larger than L2; restore copy between steps",
+                       "timing": "CUDA events around the whole distributed sort on every rank, max over ranks",
+                       "verified": verified},
+            "stages_ms_max_over_ranks": stages,
+            "exchange_gbs_per_gpu": (world - 1) / world * 4 * n / (stages["exchange"] * 1e-3) / 1e9 if world > 1 else None,
+            "e2e": {"value": world * n / (e2e_ms * 1e-3) / 1e9, "unit": unit, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": 4 * n * world, "d2h_bytes_per_step": 4 * n * world,
+                    "path": "per rank: pinned host keys -> H2D -> distributed sort (C-ABI kernels + NCCL) -> D2H of the sorted slice"},
+            "gpu_launches": launches * steps, "gpu_launches_per_step": launches,
+            "roofline": {"bound": "hbm", "achieved": 36 * n / (sort_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": 36 * n / (sort_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                         "kernel": "local sort of the received slice (whole vrdxCmdSort, 36 B/key algorithmic)",
+                         "peak_source": peak_src},
+            "cpu_baseline": None, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    backend.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0 if verified else 1
