@@ -331,8 +331,8 @@ def run_single(args):
 # ------------------------------------------------------------------------------ our arm, N > 1
 
 def run_distributed(args):
-    from vulkan_radix_sort_b200 import dist_bench
-    return dist_bench.run(args, METRIC, UNIT)
+    import bench_dist
+    return bench_dist.run(args, METRIC, UNIT)
 
 
 def main():

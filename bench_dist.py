@@ -1,4 +1,4 @@
-"""bench.py --gpus N (N > 1): BASELINE.json configs[4] — distributed keys-only sort, 2^29 uniform
+"""bench_dist.py — the N > 1 leg of bench.py (bench.py --gpus N): BASELINE.json configs[4] — distributed keys-only sort, 2^29 uniform
 keys per GPU (weak scaling), exact-splitter partition + NCCL all-to-all-v over NVLink + local
 LSD sort.  One process per GPU (launched by torch.distributed.run); rank 0 prints the JSON line.
 Timing: CUDA events on each rank's stream around the whole distributed sort, MAX over ranks."""
@@ -34,8 +34,8 @@ class _Timers:
 def run(args, metric, unit):
     from bench import ClockSampler, measured_peak_gbs  # the shared helpers live in bench.py
     from oracle import cpu_oracle
-    from .datagen import DataGenerator
-    from .dist import CudaBackend, distributed_sort
+    from vulkan_radix_sort_b200.datagen import DataGenerator
+    from vulkan_radix_sort_b200.dist import CudaBackend, distributed_sort
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
