@@ -56,8 +56,10 @@ def main():
             bpk = 68 if kv else 36
             hist = (stages[1] - stages[0]) / 1e3
             passes = [(stages[4 + 3 * i] - stages[3 + 3 * i]) / 1e3 for i in range(4)]
+            ups = [(stages[2 + 3 * i] - stages[1 + 3 * i]) / 1e3 for i in range(4)]
+            sps = [(stages[3 + 3 * i] - stages[2 + 3 * i]) / 1e3 for i in range(4)]
             print(f"N=2^{log2n} {'kv  ' if kv else 'keys'} {t/1e6:8.3f} ms  {n/t:7.2f} GKeys/s  "
-                  f"{bpk*n/t:8.1f} GB/s  hist+reset={hist:.1f}us passes={[round(x,1) for x in passes]}us",
+                  f"{bpk*n/t:8.1f} GB/s  hist+reset={hist:.1f}us up={[round(x,1) for x in ups]} sp={[round(x,1) for x in sps]} dn={[round(x,1) for x in passes]}us",
                   flush=True)
             ok = bool((keys[1:].view(torch.uint32).to(torch.int64) >= keys[:-1].view(torch.uint32).to(torch.int64)).all()) \
                 if n <= (1 << 26) else True

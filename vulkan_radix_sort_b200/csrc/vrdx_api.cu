@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <utility>
 #include <vector>
 
 #define VRDX_FORCE_VK_SHIM 1
@@ -46,6 +47,24 @@ struct PassVariant {
   cudaError_t (*launch_inorder)(cudaStream_t, uint32_t, const PassArgs&);    // onesweep, tile id = blockIdx.x (experiment)
 };
 
+// Launch with (or without) the programmatic-dependent-launch attribute; see GridDepWait().
+static bool g_pdl = true;
+template <typename... KArgs, typename... Args>
+cudaError_t LaunchEx(void (*kernel)(KArgs...), uint32_t grid, uint32_t block, size_t smem, cudaStream_t stream,
+                     bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && g_pdl) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 template <class Cfg>
 cudaError_t PrepareDirect(int* ctas_per_sm) {
   cudaError_t e = cudaFuncSetAttribute(OnesweepKernel<Cfg, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -73,19 +92,17 @@ cudaError_t PrepareTma(int* ctas_per_sm) {
 }
 template <class Cfg, int MODE>
 cudaError_t LaunchDirect(cudaStream_t stream, uint32_t grid, const PassArgs& args) {
-  OnesweepKernel<Cfg, MODE><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(args);
-  return cudaGetLastError();
+  return LaunchEx(OnesweepKernel<Cfg, MODE>, grid, Cfg::kThreads, Cfg::kSmemBytes, stream, true, args);
 }
 template <class Cfg, int MODE>
 cudaError_t LaunchTma(cudaStream_t stream, uint32_t grid, const PassArgs& args) {
-  OnesweepTmaKernel<Cfg, MODE><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(args);
-  return cudaGetLastError();
+  return LaunchEx(OnesweepTmaKernel<Cfg, MODE>, grid, Cfg::kThreads, Cfg::kSmemBytes, stream, true, args);
 }
 template <class Cfg>
 cudaError_t LaunchUpsweep(cudaStream_t stream, uint32_t grid, const PassArgs& args) {
-  UpsweepKernel<256, Cfg::kTile><<<grid, 256, 0, stream>>>(args.indirect, args.n_or_max, args.pass, args.keys_in,
-                                                          args.status);
-  return cudaGetLastError();
+  // the first kernel of a sort (pass 0) is a normal launch: it must wait for the caller's prior work
+  return LaunchEx(UpsweepKernel<Cfg::kTile>, grid, kUpsweepThreads, 0, stream, args.pass != 0, args.indirect,
+                  args.n_or_max, args.pass, args.keys_in, args.status, args.status_next, args.hdr);
 }
 template <int T, int I, bool KV, int M, int LB = 4>
 constexpr PassVariant MakeVariant() {
@@ -110,13 +127,15 @@ cudaError_t LaunchCluster(cudaStream_t stream, uint32_t grid, const PassArgs& ar
   cfg.blockDim = dim3(Cfg::kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = C;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_pdl ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, OnesweepClusterKernel<Cfg, C>, args);
 }
 template <int T, int I, bool KV, int M, int C, int LB = 4>
@@ -142,12 +161,16 @@ static const PassVariant kKeysVariants[] = {
     MakeVariant<512, 16, false, 2>(),           MakeVariant<256, 16, false, 4>(),
     MakeVariant<384, 12, false, 4>(),           MakeVariant<256, 12, false, 6>(),
     MakeClusterVariant<384, 16, false, 3, 4>(), MakeClusterVariant<384, 16, false, 3, 8>(),
+    MakeVariant<256, 16, false, 6>(),           MakeVariant<256, 20, false, 4>(),
+    MakeVariant<320, 16, false, 4>(),           MakeVariant<256, 24, false, 3>(),
 };
 static const PassVariant kPairVariants[] = {
     MakeVariant<384, 16, true, 3>(),            MakeVariant<256, 16, true, 5>(),
     MakeVariant<512, 16, true, 2>(),            MakeVariant<256, 16, true, 4>(),
     MakeVariant<384, 12, true, 4>(),            MakeVariant<256, 12, true, 6>(),
     MakeClusterVariant<384, 16, true, 3, 4>(),  MakeClusterVariant<384, 16, true, 3, 8>(),
+    MakeVariant<256, 16, true, 6>(),            MakeVariant<256, 20, true, 4>(),
+    MakeVariant<320, 16, true, 4>(),            MakeVariant<256, 24, true, 3>(),
 };
 constexpr int kDefaultKeysRtsVariant = 1;
 constexpr int kDefaultPairRtsVariant = 0;
@@ -302,8 +325,8 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
     uint64_t chunks = CeilDiv(n_or_max, (uint64_t)kHistChunk);
     uint64_t cap = (uint64_t)sorter->sm_count * 4;
     uint32_t grid = (uint32_t)(chunks < cap ? (chunks ? chunks : 1) : cap);
-    HistogramKernel<<<grid, kHistThreads, 0, stream>>>(keys, indirect, n_or_max, hdr);
-    NoteError(sorter, cudaGetLastError());
+    NoteError(sorter, LaunchEx(HistogramKernel, grid, kHistThreads, 0, stream, false, (const uint32_t*)keys, indirect,
+                               n_or_max, hdr));
     ++launches;
   }  // reduce-then-scan keeps no state across passes: every table it reads is written first
   Stamp(sorter, stream, queryPool, query + 1);
@@ -326,17 +349,20 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
       // the reference's three stages: status A = [tile][256] histograms -> exclusive prefixes,
       // status B = spine chunk sums; timestamps fall exactly where the reference puts them
       args.status = status[0];
-      args.status_next = nullptr;
+      args.status_next = status[1];
       const uint32_t chunks = (uint32_t)CeilDiv(tiles, (uint64_t)kSpineChunk);
-      NoteError(sorter, variant.launch_upsweep(stream, tiles, args));
+      NoteError(sorter, variant.launch_upsweep(stream, chunks, args));
       Stamp(sorter, stream, queryPool, query + 2 + 3 * pass + 0);
-      SpineReduceKernel<<<chunks, kRadix, 0, stream>>>(indirect, n_or_max, variant.tile, status[0], status[1]);
-      SpineScanKernel<<<1, kRadix, 0, stream>>>(indirect, n_or_max, variant.tile, pass, status[1], hdr);
-      SpineApplyKernel<<<chunks, kRadix, 0, stream>>>(indirect, n_or_max, variant.tile, status[0], status[1]);
-      NoteError(sorter, cudaGetLastError());
+      // spine scratch: chunk prefixes occupy rows [0, chunks) of status B, segment sums the rows after them
+      uint32_t* seg = status[1] + (size_t)chunks * kRadix;
+      const uint32_t seg_grid = chunks < (uint32_t)kSpineSegments ? (chunks ? chunks : 1u) : (uint32_t)kSpineSegments;
+      NoteError(sorter, LaunchEx(SpineReduceKernel, seg_grid, (uint32_t)kRadix, 0, stream, true, indirect,
+                                 n_or_max, variant.tile, pass, (const uint32_t*)status[1], seg, hdr));
+      NoteError(sorter, LaunchEx(SpineApplyKernel, seg_grid, (uint32_t)kRadix, 0, stream, true, indirect,
+                                 n_or_max, variant.tile, status[1], (const uint32_t*)seg));
       Stamp(sorter, stream, queryPool, query + 2 + 3 * pass + 1);
       NoteError(sorter, variant.launch_downsweep(stream, use_tma ? pass_grid : tiles, args));
-      launches += 5;
+      launches += 4;
       Stamp(sorter, stream, queryPool, query + 2 + 3 * pass + 2);
       continue;
     }
@@ -434,6 +460,7 @@ VkResult vrdxCudaCreateSorter(const VrdxSorterCreateInfo* pCreateInfo,
   s->pair_tma_ctas = pair_tma_ctas;
   s->tile_load = tile_load;
   if (const char* e = getenv("VRDX_ALGORITHM")) s->algorithm = (VrdxCudaAlgorithm)atoi(e);
+  if (const char* e = getenv("VRDX_PDL")) g_pdl = atoi(e) != 0;
   if (pOptions && pOptions->structSize >= sizeof(VrdxCudaSorterOptions) &&
       pOptions->algorithm != VRDX_CUDA_ALGORITHM_AUTO)
     s->algorithm = pOptions->algorithm;

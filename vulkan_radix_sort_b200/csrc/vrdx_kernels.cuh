@@ -36,6 +36,12 @@ __device__ __forceinline__ void StRelaxed(uint32_t* p, uint32_t v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t LdStream(const uint32_t* p) { return __ldcs(p); }
+// Programmatic dependent launch (sm_90+): every kernel of a sort lets its successor start launching
+// at once (GridDepLaunch) and waits for its predecessor's memory only where it first needs it
+// (GridDepWait), so launch latency, CTA ramp-up and prologues overlap the previous kernel's tail.
+// Both are no-ops when the kernel was launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void GridDepLaunch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void GridDepWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ uint32_t LaneMaskLt() {
   uint32_t m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -81,6 +87,7 @@ HistogramKernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ 
   __shared__ uint32_t sh[kPasses][kRadix];
   __shared__ uint32_t s_last;
   const int tid = threadIdx.x;
+  GridDepLaunch();
   const uint32_t n = ResolveCount(indirect, n_or_max);
 
   for (int i = tid; i < kPasses * kRadix; i += kHistThreads) (&sh[0][0])[i] = 0;
@@ -177,13 +184,15 @@ struct PassArgs {
   uint32_t pass;              // 0..3
   StorageHeader* hdr;
   uint32_t* status;           // look-back cells of this pass: [tile][256]
-  uint32_t* status_next;      // cells of the next pass, cleared here (nullptr on the last pass)
+  uint32_t* status_next;      // onesweep: cells of the next pass, cleared here (nullptr on the last pass);
+                              // reduce-then-scan: scanned chunk prefixes [chunk][256]
   const uint32_t* keys_in;
   uint32_t* keys_out;
   const uint32_t* vals_in;
   uint32_t* vals_out;
 };
 
+constexpr int kSpineChunk = 8;         // reduce-then-scan: tiles per upsweep CTA / spine chunk
 constexpr int kRepairBallotThreshold = 12;  // colliding lanes above which the 8-round ballot loop is cheaper
 
 template <int THREADS, int IPT, bool KV, int MIN_CTAS, int LOOK_BATCH = 4>
@@ -316,15 +325,16 @@ OnesweepKernel(const PassArgs a) {
   const int warp = tid >> 5;
   const uint32_t shift = a.pass * kRadixBits;
   const uint32_t n = ResolveCount(a.indirect, a.n_or_max);
-
-  // Tile ids are handed out in arrival order so that every predecessor a tile may wait on in
-  // the look-back is already resident (forward progress without relying on blockIdx order).
-  if (MODE == 0 && tid == 0) s_misc[8] = atomicAdd(&a.hdr->tickets[a.pass], 1u);  // MODE 1/2: blockIdx.x
+  GridDepLaunch();
   {
     uint4* z = reinterpret_cast<uint4*>(s_cnt);
 #pragma unroll
     for (int j = tid; j < kWarps * kRadix / 4; j += THREADS) z[j] = make_uint4(0u, 0u, 0u, 0u);
   }
+  GridDepWait();  // everything below reads what the previous kernel of this sort wrote
+  // Tile ids are handed out in arrival order so that every predecessor a tile may wait on in
+  // the look-back is already resident (forward progress without relying on blockIdx order).
+  if (MODE == 0 && tid == 0) s_misc[8] = atomicAdd(&a.hdr->tickets[a.pass], 1u);  // MODE 1/2: blockIdx.x
   __syncthreads();
 
   const uint32_t tile = (MODE == 0) ? s_misc[8] : blockIdx.x;
@@ -403,7 +413,17 @@ OnesweepKernel(const PassArgs a) {
         look_s[j] = (tile > 0) ? LdRelaxed(a.status + (size_t)t * kRadix + tid) : 0u;
       }
     } else {
-      look_s[0] = a.status[(size_t)tile * kRadix + tid];  // exclusive prefix over earlier tiles (spine)
+      // reduce-then-scan: scanned chunk prefix + the rows of the earlier tiles of this chunk
+      const uint32_t chunk = tile / kSpineChunk;
+      const uint32_t in_chunk = tile % kSpineChunk;
+      const uint32_t* row = a.status + (size_t)chunk * kSpineChunk * kRadix + tid;
+      uint32_t part[kSpineChunk - 1];
+#pragma unroll
+      for (int j = 0; j < kSpineChunk - 1; ++j) part[j] = ((uint32_t)j < in_chunk) ? row[(size_t)j * kRadix] : 0u;  // all in flight at once
+      uint32_t acc = a.status_next[(size_t)chunk * kRadix + tid];
+#pragma unroll
+      for (int j = 0; j < kSpineChunk - 1; ++j) acc += part[j];
+      look_s[0] = acc;
     }
   }
   __syncthreads();
@@ -503,13 +523,15 @@ OnesweepClusterKernel(const PassArgs a) {
   const uint32_t shift = a.pass * kRadixBits;
   const uint32_t n = ResolveCount(a.indirect, a.n_or_max);
 
-  // one ticket per cluster, drawn by rank 0 and read by the other CTAs over DSMEM
-  if (crank == 0 && tid == 0) s_misc[8] = atomicAdd(&a.hdr->tickets[a.pass], 1u);
+  GridDepLaunch();
   {
     uint4* z = reinterpret_cast<uint4*>(s_cnt);
 #pragma unroll
     for (int j = tid; j < kWarps * kRadix / 4; j += THREADS) z[j] = make_uint4(0u, 0u, 0u, 0u);
   }
+  GridDepWait();
+  // one ticket per cluster, drawn by rank 0 and read by the other CTAs over DSMEM
+  if (crank == 0 && tid == 0) s_misc[8] = atomicAdd(&a.hdr->tickets[a.pass], 1u);
   cluster.sync();
   const uint32_t ctile = *cluster.map_shared_rank(&s_misc[8], 0);
   const uint64_t cluster_start = (uint64_t)ctile * CLUSTER * kTile;
@@ -649,77 +671,123 @@ OnesweepClusterKernel(const PassArgs a) {
 // ------------------------------------------------------------------------------------------
 // Reduce-then-scan variant (the reference's upsweep / spine / downsweep decomposition,
 // src/shader/upsweep.slang, spine.slang, downsweep.slang), kept for A/B measurement against the
-// single-pass look-back and as the path for N >= 2^30 (full 32-bit counts, no flag bits).
-// Per pass: UpsweepKernel (4 B/key read) -> 3 small spine kernels over the [tile][256] table ->
-// OnesweepKernel<Cfg, 1> (4 B/key read + 4 B/key write).  Algorithmic overhead vs onesweep:
-// the keys are read twice per pass (12 instead of 8 B/key/pass).
+// single-pass look-back and as the path for N >= 2^30 (full 32-bit counts, no flag bits).  On
+// B200 it is the faster composition from N ~ 2^25 up (profiles/r01_sweep_n.txt): the scatter pass
+// has no inter-CTA dependency at all.  Per pass, four launches:
+//   UpsweepKernel    4 B/key read; one CTA counts a CHUNK of kSpineChunk consecutive tiles and
+//                    writes tile_hist[tile][256] plus the chunk's column sums chunk_sums[chunk][256]
+//   SpineReduceKernel + SpineApplyKernel  exclusive scan of chunk_sums over chunks (coalesced,
+//                    segment-parallel) + global digit offsets (last CTA done)
+//   OnesweepKernel<Cfg, 1>  4 B/key read + 4 B/key write; a tile's offset for digit d is
+//                    chunk_sums[chunk][d] + the tile_hist rows of the <= kSpineChunk-1 earlier
+//                    tiles of its chunk, fetched while the tile is being reordered
+// Algorithmic overhead vs onesweep: the keys are read twice per pass (12 instead of 8 B/key).
 // ------------------------------------------------------------------------------------------
-template <int THREADS, int TILE>
-__global__ void __launch_bounds__(THREADS)
+constexpr int kUpsweepThreads = 256;
+
+template <int TILE>
+__global__ void __launch_bounds__(kUpsweepThreads)
 UpsweepKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t pass,
-              const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ tile_hist) {
-  __shared__ uint32_t h[kRadix];
+              const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ tile_hist,
+              uint32_t* __restrict__ chunk_sums, StorageHeader* __restrict__ hdr) {
+  constexpr int THREADS = kUpsweepThreads;
+  static_assert(THREADS == kRadix, "one thread per digit");
+  __shared__ uint32_t h[2][kRadix];
   const int tid = threadIdx.x;
+  GridDepLaunch();
   const uint32_t n = ResolveCount(indirect, n_or_max);
-  const uint32_t tile = blockIdx.x;
-  const uint64_t tile_start = (uint64_t)tile * TILE;
-  if (tile_start >= n) return;
-  const uint32_t remaining = (uint32_t)(n - tile_start);
-  const uint32_t tile_count = remaining < (uint32_t)TILE ? remaining : (uint32_t)TILE;
-  const uint32_t shift = pass * kRadixBits;
-  for (int i = tid; i < kRadix; i += THREADS) h[i] = 0;
-  __syncthreads();
-  const uint32_t* kin = keys_in + tile_start;
-  constexpr int kIters = (TILE + THREADS - 1) / THREADS;
-  uint32_t k[kIters];
-#pragma unroll
-  for (int i = 0; i < kIters; ++i) {
-    const uint32_t idx = i * THREADS + tid;
-    k[i] = idx < tile_count ? LdStream(kin + idx) : 0u;
-  }
-#pragma unroll
-  for (int i = 0; i < kIters; ++i) {
-    const uint32_t idx = i * THREADS + tid;
-    if (idx < tile_count) atomicAdd(&h[(k[i] >> shift) & 0xFFu], 1u);
-  }
-  __syncthreads();
-  for (int i = tid; i < kRadix; i += THREADS) tile_hist[(size_t)tile * kRadix + i] = h[i];
-}
-
-constexpr int kSpineChunk = 128;  // tiles per spine chunk
-
-// chunk_sums[c][d] = sum over the tiles of chunk c of tile_hist[t][d]
-__global__ void __launch_bounds__(kRadix)
-SpineReduceKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t tile_size,
-                  const uint32_t* __restrict__ tile_hist, uint32_t* __restrict__ chunk_sums) {
-  const uint32_t n = ResolveCount(indirect, n_or_max);
-  const uint32_t tiles = (uint32_t)CeilDiv(n, tile_size);
+  const uint32_t tiles = (uint32_t)CeilDiv(n, (uint64_t)TILE);
   const uint32_t first = blockIdx.x * kSpineChunk;
+  h[0][tid] = 0;
+  h[1][tid] = 0;
+  GridDepWait();
+  if (blockIdx.x == 0 && tid == 0) hdr->hist_blocks_done = 0;  // counter of this pass's SpineScanKernel
   if (first >= tiles) return;
   const uint32_t last = first + kSpineChunk < tiles ? first + kSpineChunk : tiles;
-  uint32_t sum = 0;
-  for (uint32_t t = first; t < last; ++t) sum += tile_hist[(size_t)t * kRadix + threadIdx.x];
-  chunk_sums[(size_t)blockIdx.x * kRadix + threadIdx.x] = sum;
+  const uint32_t shift = pass * kRadixBits;
+  constexpr int kIters = (TILE + THREADS - 1) / THREADS;
+  uint32_t chunk_acc = 0;
+  __syncthreads();
+  for (uint32_t tile = first; tile < last; ++tile) {
+    uint32_t* hh = h[(tile - first) & 1];
+    const uint64_t tile_start = (uint64_t)tile * TILE;
+    const uint32_t remaining = (uint32_t)(n - tile_start);
+    const uint32_t tile_count = remaining < (uint32_t)TILE ? remaining : (uint32_t)TILE;
+    const uint32_t* kin = keys_in + tile_start;
+    uint32_t k[kIters];
+    if (tile_count == (uint32_t)TILE) {
+#pragma unroll
+      for (int i = 0; i < kIters; ++i) k[i] = LdStream(kin + i * THREADS + tid);
+#pragma unroll
+      for (int i = 0; i < kIters; ++i) atomicAdd(&hh[(k[i] >> shift) & 0xFFu], 1u);
+    } else {
+#pragma unroll
+      for (int i = 0; i < kIters; ++i) {
+        const uint32_t idx = i * THREADS + tid;
+        if (idx < tile_count) atomicAdd(&hh[(LdStream(kin + idx) >> shift) & 0xFFu], 1u);
+      }
+    }
+    __syncthreads();  // one barrier per tile: the two histograms alternate
+    const uint32_t c = hh[tid];
+    hh[tid] = 0;      // ready for tile + 2 (the next tile uses the other buffer; barrier above orders it)
+    tile_hist[(size_t)tile * kRadix + tid] = c;
+    chunk_acc += c;
+  }
+  chunk_sums[(size_t)blockIdx.x * kRadix + tid] = chunk_acc;
 }
 
-// in-place exclusive scan of chunk_sums over chunks, one thread per digit (spine.slang:32-60);
-// the per-digit totals then give the global digit offsets of this pass (spine.slang:62-83), so
-// the reduce-then-scan path needs no separate histogram kernel.
-__global__ void __launch_bounds__(kRadix)
-SpineScanKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t tile_size, uint32_t pass,
-                uint32_t* __restrict__ chunk_sums, StorageHeader* __restrict__ hdr) {
-  __shared__ uint32_t s_warp[kRadix / 32];
-  const uint32_t n = ResolveCount(indirect, n_or_max);
+// Spine: exclusive scan of chunk_sums[chunk][256] over chunks for every digit, and the global
+// digit offsets of this pass (spine.slang:32-60 and :62-83).  Two coalesced kernels (thread =
+// digit, so every row access is one 1 KB line):
+//   SpineReduceKernel  CTA s sums the rows of segment s -> seg[s][256]; the LAST CTA to finish
+//                      scans seg over segments in place and turns the per-digit totals into the
+//                      global digit offsets hdr->global_hist[pass]
+//   SpineApplyKernel   CTA s rewrites the rows of segment s as exclusive prefixes
+constexpr int kSpineSegments = 128;
+
+// The grid (number of segments) is sized by the host from maxElementCount; the rows are split
+// evenly over however many segments were launched, using the device-resident count.
+__device__ __forceinline__ void SpineGeometry(uint32_t n, uint32_t tile_size, uint32_t& chunks, uint32_t& rows_per) {
   const uint32_t tiles = (uint32_t)CeilDiv(n, tile_size);
-  const uint32_t chunks = (uint32_t)CeilDiv(tiles, kSpineChunk);
+  chunks = (uint32_t)CeilDiv(tiles, kSpineChunk);
+  rows_per = (chunks + gridDim.x - 1) / gridDim.x;
+}
+
+__global__ void __launch_bounds__(kRadix)
+SpineReduceKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t tile_size, uint32_t pass,
+                  const uint32_t* __restrict__ chunk_sums, uint32_t* __restrict__ seg, StorageHeader* __restrict__ hdr) {
+  __shared__ uint32_t s_last;
+  __shared__ uint32_t s_warp[kRadix / 32];
+  GridDepLaunch();
+  GridDepWait();
+  const uint32_t n = ResolveCount(indirect, n_or_max);
+  uint32_t chunks, rows_per;
+  SpineGeometry(n, tile_size, chunks, rows_per);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t r0 = blockIdx.x * rows_per;
+  const uint32_t r1 = r0 + rows_per < chunks ? r0 + rows_per : chunks;
+  uint32_t sum = 0;
+#pragma unroll 8
+  for (uint32_t r = r0; r < r1; ++r) sum += chunk_sums[(size_t)r * kRadix + tid];
+  seg[(size_t)blockIdx.x * kRadix + tid] = sum;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&hdr->hist_blocks_done, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
   uint32_t run = 0;
-  for (uint32_t c = 0; c < chunks; ++c) {
-    const uint32_t v = chunk_sums[(size_t)c * kRadix + tid];
-    chunk_sums[(size_t)c * kRadix + tid] = run;
-    run += v;
+  for (uint32_t s0 = 0; s0 < gridDim.x; s0 += 32) {  // 32 rows in flight per round trip
+    uint32_t v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = (s0 + j < gridDim.x) ? __ldcg(seg + (size_t)(s0 + j) * kRadix + tid) : 0u;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (s0 + j < gridDim.x) seg[(size_t)(s0 + j) * kRadix + tid] = run;
+      run += v[j];
+    }
   }
-  // run == number of keys with digit `tid`; exclusive scan over digits
+  // run == number of keys with digit `tid`: exclusive scan over digits -> global digit offsets
   const uint32_t incl = WarpInclusiveScan(run, lane);
   if (lane == 31) s_warp[warp] = incl;
   __syncthreads();
@@ -730,19 +798,22 @@ SpineScanKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32
   if (tid == 0 && pass == 0) hdr->element_count[0] = n;
 }
 
-// tile_hist[t][d] <- exclusive prefix over tiles of digit d (in place)
 __global__ void __launch_bounds__(kRadix)
 SpineApplyKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t tile_size,
-                 uint32_t* __restrict__ tile_hist, const uint32_t* __restrict__ chunk_sums) {
+                 uint32_t* __restrict__ chunk_sums, const uint32_t* __restrict__ seg) {
+  GridDepLaunch();
+  GridDepWait();
   const uint32_t n = ResolveCount(indirect, n_or_max);
-  const uint32_t tiles = (uint32_t)CeilDiv(n, tile_size);
-  const uint32_t first = blockIdx.x * kSpineChunk;
-  if (first >= tiles) return;
-  const uint32_t last = first + kSpineChunk < tiles ? first + kSpineChunk : tiles;
-  uint32_t run = chunk_sums[(size_t)blockIdx.x * kRadix + threadIdx.x];
-  for (uint32_t t = first; t < last; ++t) {
-    const uint32_t v = tile_hist[(size_t)t * kRadix + threadIdx.x];
-    tile_hist[(size_t)t * kRadix + threadIdx.x] = run;
+  uint32_t chunks, rows_per;
+  SpineGeometry(n, tile_size, chunks, rows_per);
+  const int tid = threadIdx.x;
+  const uint32_t r0 = blockIdx.x * rows_per;
+  const uint32_t r1 = r0 + rows_per < chunks ? r0 + rows_per : chunks;
+  uint32_t run = seg[(size_t)blockIdx.x * kRadix + tid];
+#pragma unroll 8
+  for (uint32_t r = r0; r < r1; ++r) {
+    const uint32_t v = chunk_sums[(size_t)r * kRadix + tid];
+    chunk_sums[(size_t)r * kRadix + tid] = run;
     run += v;
   }
 }
@@ -847,6 +918,8 @@ OnesweepTmaKernel(const PassArgs a) {
     }
   };
 
+  GridDepLaunch();
+  GridDepWait();
   if (tid == kProducer) {
     MbarInit(&s_bar[0], 1);
     MbarInit(&s_bar[1], 1);
@@ -942,7 +1015,16 @@ OnesweepTmaKernel(const PassArgs a) {
           look_s[j] = (tile > 0) ? LdRelaxed(a.status + (size_t)t * kRadix + tid) : 0u;
         }
       } else {
-        look_s[0] = a.status[(size_t)tile * kRadix + tid];  // exclusive prefix over earlier tiles (spine)
+        const uint32_t chunk = tile / kSpineChunk;
+        const uint32_t in_chunk = tile % kSpineChunk;
+        const uint32_t* row = a.status + (size_t)chunk * kSpineChunk * kRadix + tid;
+        uint32_t part[kSpineChunk - 1];
+#pragma unroll
+        for (int j = 0; j < kSpineChunk - 1; ++j) part[j] = ((uint32_t)j < in_chunk) ? row[(size_t)j * kRadix] : 0u;
+        uint32_t acc = a.status_next[(size_t)chunk * kRadix + tid];
+#pragma unroll
+        for (int j = 0; j < kSpineChunk - 1; ++j) acc += part[j];
+        look_s[0] = acc;
       }
     }
     // the id of the tile that will replace this one is drawn here, off the critical path
