@@ -35,7 +35,7 @@ def run(args, metric, unit):
     from bench import ClockSampler, measured_peak_gbs  # the shared helpers live in bench.py
     from oracle import cpu_oracle
     from vulkan_radix_sort_b200.datagen import DataGenerator
-    from vulkan_radix_sort_b200.dist import CudaBackend, distributed_sort
+    from vulkan_radix_sort_b200.dist import CudaBackend, SharedReceive, distributed_sort
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
@@ -52,8 +52,10 @@ def run(args, metric, unit):
     keys = torch.empty_like(pristine)
     backend = CudaBackend(local_rank)
     cap = n + (n >> 6) + 1024                                    # exact splitters: every rank receives N/G +- 1
-    part = torch.empty(n, dtype=torch.int32, device="cuda")
-    recv = torch.empty(cap, dtype=torch.int32, device="cuda")
+    fused = os.environ.get("VRDX_DIST_EXCHANGE", "fused") != "nccl"
+    shared = SharedReceive(backend, cap) if fused else None
+    part = None if fused else torch.empty(n, dtype=torch.int32, device="cuda")
+    recv = shared.tensor if fused else torch.empty(cap, dtype=torch.int32, device="cuda")
     storage = backend.storage_for(cap)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -67,7 +69,8 @@ def run(args, metric, unit):
         dist.barrier()
         torch.cuda.synchronize()
         tm = _Timers()
-        _, recv_count, plan = distributed_sort(backend, keys, n, recv=recv, part=part, storage=storage, timers=tm)
+        _, recv_count, plan = distributed_sort(backend, keys, n, recv=recv, part=part, storage=storage, timers=tm,
+                                               shared=shared)
         torch.cuda.synchronize()
         dist.barrier()
         if it >= warmup:
@@ -113,7 +116,7 @@ def run(args, metric, unit):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         keys.copy_(pinned_in, non_blocking=True)
-        _, rc, _ = distributed_sort(backend, keys, n, recv=recv, part=part, storage=storage)
+        _, rc, _ = distributed_sort(backend, keys, n, recv=recv, part=part, storage=storage, shared=shared)
         pinned_out[:rc].copy_(recv[:rc], non_blocking=True)
         e1.record()
         torch.cuda.synchronize()
@@ -135,13 +138,18 @@ def run(args, metric, unit):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"distributed 32-bit keys-only sort, 2^{args.log2n_per_gpu} uniform keys per GPU "
-                                   f"(DataGenerator seed 1+rank), {world} GPUs: exact-splitter MSD partition + NCCL "
-                                   f"all-to-all-v + local LSD sort",
+                                   f"(DataGenerator seed 1+rank), {world} GPUs: exact-splitter MSD partition "
+                                   + ("fused with the exchange (peer stores over NVLink)" if fused else "+ NCCL all-to-all-v")
+                                   + " + local LSD sort",
                        "l2": "per-GPU inputs (2 GiB) larger than L2; restore copy between steps",
                        "timing": "CUDA events around the whole distributed sort on every rank, max over ranks",
                        "verified": verified},
             "stages_ms_max_over_ranks": stages,
-            "exchange_gbs_per_gpu": (world - 1) / world * 4 * n / (stages["exchange"] * 1e-3) / 1e9 if world > 1 else None,
+            # bytes leaving each GPU / time of the stage(s) that move them (fused: partition + barrier)
+            "exchange_gbs_per_gpu": ((world - 1) / world * 4 * n /
+                                     ((stages["exchange"] + (stages["partition"] if fused else 0.0)) * 1e-3) / 1e9)
+            if world > 1 else None,
+            "exchange": "fused peer stores (CUDA IPC over NVLink)" if fused else "NCCL all-to-all-v",
             "e2e": {"value": world * n / (e2e_ms * 1e-3) / 1e9, "unit": unit, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 4 * n * world, "d2h_bytes_per_step": 4 * n * world,
                     "path": "per rank: pinned host keys -> H2D -> distributed sort (C-ABI kernels + NCCL) -> D2H of the sorted slice"},
@@ -153,6 +161,8 @@ def run(args, metric, unit):
             "cpu_baseline": None, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
+    if shared is not None:
+        shared.close()
     backend.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -21,13 +21,15 @@ extern "C" {
 
 /*
  * One level of the distributed splitter search.  For every prefix j < prefixCount, counts the keys
- * whose bits above (shift + 8) equal prefixes[j] by their 8-bit digit at `shift`:
- *     histogram[j][d] += #{ i < elementCount : (key_i >> (shift+8)) == prefixes[j]  &&  ((key_i >> shift) & 255) == d }
- * (shift = 24: the prefix is empty and every key is counted).  `histogram` (prefixCount x 256
- * uint32) must be zeroed by the caller.  prefixCount <= VRDX_DIST_MAX_SPLITTERS.
+ * whose bits above (shift + digitBits) equal prefixes[j] by their digitBits-wide digit at `shift`:
+ *     histogram[j][d] += #{ i < elementCount : (key_i >> (shift+digitBits)) == prefixes[j]
+ *                                              &&  ((key_i >> shift) & (2^digitBits - 1)) == d }
+ * (shift + digitBits = 32: the prefix is empty and every key is counted).  `histogram`
+ * (prefixCount x 2^digitBits uint32) must be zeroed by the caller.  digitBits in [1, 12],
+ * prefixCount <= VRDX_DIST_MAX_SPLITTERS and prefixCount * 2^digitBits * 4 bytes <= 160 KiB.
  */
 void vrdxDistCmdPrefixHistogram(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t elementCount,
-                                VkBuffer keysBuffer, VkDeviceSize keysOffset, uint32_t shift,
+                                VkBuffer keysBuffer, VkDeviceSize keysOffset, uint32_t shift, uint32_t digitBits,
                                 uint32_t prefixCount, VkBuffer prefixesBuffer, VkDeviceSize prefixesOffset,
                                 VkBuffer histogramBuffer, VkDeviceSize histogramOffset);
 
@@ -42,6 +44,30 @@ void vrdxDistCmdPartition(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint
                           VkBuffer keysBuffer, VkDeviceSize keysOffset, uint32_t splitterCount,
                           VkBuffer splittersBuffer, VkDeviceSize splittersOffset, VkBuffer cursorsBuffer,
                           VkDeviceSize cursorsOffset, VkBuffer outBuffer, VkDeviceSize outOffset);
+
+/*
+ * Partition + exchange in ONE kernel.  Same multi-split as vrdxDistCmdPartition, but a key whose
+ * class-ordered position is p, with firstPosition[j] <= p < firstPosition[j+1], is stored straight
+ * into destination j's receive buffer at destPointers[j][p - firstPosition[j]] — peer memory
+ * mapped with vrdxDistOpenShared(), i.e. the stores travel over NVLink / NVSwitch while the kernel
+ * is still ranking other tiles.  No separate all-to-all; the caller only needs a barrier across
+ * ranks before anyone reads its receive buffer.
+ * destTable (device memory): uint64 destPointers[destCount] followed by uint32 firstPosition[destCount + 1].
+ */
+void vrdxDistCmdPartitionScatter(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t elementCount,
+                                 VkBuffer keysBuffer, VkDeviceSize keysOffset, uint32_t splitterCount,
+                                 VkBuffer splittersBuffer, VkDeviceSize splittersOffset, VkBuffer cursorsBuffer,
+                                 VkDeviceSize cursorsOffset, uint32_t destCount, VkBuffer destTableBuffer,
+                                 VkDeviceSize destTableOffset);
+
+/* Device memory that other processes on the node can map (cudaMalloc + CUDA IPC). */
+#define VRDX_DIST_IPC_HANDLE_BYTES 64
+VkResult vrdxDistAllocShared(VkDevice device, VkDeviceSize size, VkBuffer* pBuffer,
+                             unsigned char handle[VRDX_DIST_IPC_HANDLE_BYTES]);
+void vrdxDistFreeShared(VkDevice device, VkBuffer buffer);
+VkResult vrdxDistOpenShared(VkDevice device, const unsigned char handle[VRDX_DIST_IPC_HANDLE_BYTES],
+                            VkBuffer* pBuffer);
+void vrdxDistCloseShared(VkDevice device, VkBuffer buffer);
 
 #ifdef __cplusplus
 }

@@ -17,14 +17,15 @@ def _u32(t: torch.Tensor, count: int) -> np.ndarray:
 class NumpyBackend:
     device = torch.device("cpu")
 
-    def prefix_histogram(self, keys, count, shift, prefixes):
+    def prefix_histogram(self, keys, count, shift, bits, prefixes):
         k = _u32(keys, count).astype(np.uint64)
-        out = np.zeros((int(prefixes.numel()), 256), dtype=np.int64)
-        digit = ((k >> np.uint64(shift)) & np.uint64(255)).astype(np.int64)
-        hi = k >> np.uint64(shift + 8)
+        bins = 1 << bits
+        out = np.zeros((int(prefixes.numel()), bins), dtype=np.int64)
+        digit = ((k >> np.uint64(shift)) & np.uint64(bins - 1)).astype(np.int64)
+        hi = k >> np.uint64(shift + bits)
         for j, p in enumerate(prefixes.tolist()):
-            sel = np.ones(k.size, dtype=bool) if shift >= 24 else hi == np.uint64(p)
-            out[j] = np.bincount(digit[sel], minlength=256)
+            sel = np.ones(k.size, dtype=bool) if shift + bits >= 32 else hi == np.uint64(p)
+            out[j] = np.bincount(digit[sel], minlength=bins)
         return torch.from_numpy(out)
 
     def partition(self, keys, count, splitters, class_starts, out):

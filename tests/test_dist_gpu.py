@@ -36,12 +36,14 @@ def test_prefix_histogram_matches_numpy(backends, dist_name):
     for n in (1, 4099, 1000003):
         k = make_keys(dist_name, n, seed=3)
         kt = torch.from_numpy(k.view(np.int32).copy())
-        for shift, prefixes in ((24, [0]), (16, [int(k[0]) >> 24, 0xFF, 0]), (8, [int(k[n // 2]) >> 16, 1]),
-                                (0, [int(k[-1]) >> 8, int(k[0]) >> 8, 0xFFFFFF])):
+        for shift, bits, prefixes in ((24, 8, [0]), (16, 8, [int(k[0]) >> 24, 0xFF, 0]), (8, 8, [int(k[n // 2]) >> 16, 1]),
+                                      (0, 8, [int(k[-1]) >> 8, int(k[0]) >> 8, 0xFFFFFF]),
+                                      (12, 12, [int(k[0]) >> 24, 0xFF, 0, 1, 2, 3, 4]),
+                                      (0, 12, [int(k[-1]) >> 12, int(k[0]) >> 12, 0xFFFFF])):
             p = torch.tensor(prefixes, dtype=torch.int64)
-            want = np_b.prefix_histogram(kt, n, shift, p)
-            got = cuda_b.prefix_histogram(_dev(k), n, shift, p.cuda()).cpu()
-            assert torch.equal(got, want), (dist_name, n, shift)
+            want = np_b.prefix_histogram(kt, n, shift, bits, p)
+            got = cuda_b.prefix_histogram(_dev(k), n, shift, bits, p.cuda()).cpu()
+            assert torch.equal(got, want), (dist_name, n, shift, bits)
 
 
 @pytest.mark.parametrize("dist_name", ["uniform", "bits4", "all_zero", "sentinel_mix"])
@@ -66,7 +68,7 @@ def test_partition_groups_by_class(backends, dist_name):
             assert np.array_equal(np.sort(got[a:a + sz]), np.sort(k[cls == c])), (dist_name, n, c)
 
 
-def _nccl_worker(rank, world, port, dist_name, n, q):
+def _nccl_worker(rank, world, port, dist_name, n, q, fused=False):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -74,19 +76,25 @@ def _nccl_worker(rank, world, port, dist_name, n, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         from vulkan_radix_sort_b200.datagen import make_keys
-        from vulkan_radix_sort_b200.dist import CudaBackend, distributed_sort
+        from vulkan_radix_sort_b200.dist import CudaBackend, SharedReceive, distributed_sort
         k = make_keys(dist_name, n + 13 * rank, seed=1 + rank)
         backend = CudaBackend(rank)
-        recv, cnt, plan = distributed_sort(backend, torch.from_numpy(k.view(np.int32).copy()).cuda(), k.size)
-        torch.cuda.synchronize()
+        shared = SharedReceive(backend, n + 13 * world + 64) if fused else None
+        for _ in range(2):  # twice: the receive buffers are reused across sorts
+            recv, cnt, plan = distributed_sort(backend, torch.from_numpy(k.view(np.int32).copy()).cuda(), k.size,
+                                               shared=shared)
+            torch.cuda.synchronize()
         q.put((rank, k, recv[:cnt].cpu().numpy().view(np.uint32).copy(), plan.targets))
+        if shared is not None:
+            shared.close()
         backend.close()
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("fused", [False, True], ids=["nccl_all_to_all", "fused_peer_stores"])
 @pytest.mark.parametrize("dist_name", ["uniform", "all_zero", "skewed"])
-def test_distributed_sort_over_nccl(oracle, dist_name):
+def test_distributed_sort_over_nccl(oracle, dist_name, fused):
     world = torch.cuda.device_count()
     if world < 2:
         pytest.skip("needs at least two GPUs")
@@ -96,7 +104,7 @@ def test_distributed_sort_over_nccl(oracle, dist_name):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, dist_name, 3_000_017, q)) for r in range(world)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, dist_name, 3_000_017, q, fused)) for r in range(world)]
     for p in procs:
         p.start()
     results = sorted([q.get(timeout=300) for _ in range(world)], key=lambda r: r[0])

@@ -83,8 +83,14 @@ _SIGNATURES = {
     "vrdxCudaReleaseImportedMemory": (None, [c_void_p]),
     "vrdxCudaGetSorterProperties": (None, [c_void_p, POINTER(VrdxCudaSorterProperties)]),
     # include/vrdx_dist.h
-    "vrdxDistCmdPrefixHistogram": (None, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_uint32, c_uint32,
+    "vrdxDistCmdPrefixHistogram": (None, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_uint32, c_uint32, c_uint32,
                                           c_void_p, c_uint64, c_void_p, c_uint64]),
+    "vrdxDistCmdPartitionScatter": (None, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_uint32, c_void_p, c_uint64,
+                                           c_void_p, c_uint64, c_uint32, c_void_p, c_uint64]),
+    "vrdxDistAllocShared": (c_int, [c_void_p, c_uint64, POINTER(c_void_p), ctypes.c_char_p]),
+    "vrdxDistFreeShared": (None, [c_void_p, c_void_p]),
+    "vrdxDistOpenShared": (c_int, [c_void_p, ctypes.c_char_p, POINTER(c_void_p)]),
+    "vrdxDistCloseShared": (None, [c_void_p, c_void_p]),
     "vrdxDistCmdPartition": (None, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_uint32, c_void_p, c_uint64,
                                     c_void_p, c_uint64, c_void_p, c_uint64]),
 }

@@ -684,12 +684,14 @@ void vrdxCudaGetSorterProperties(VrdxSorter sorter, VrdxCudaSorterProperties* p)
 // ---------------------------------------------------------------------------- multi-GPU building blocks
 
 void vrdxDistCmdPrefixHistogram(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t elementCount,
-                                VkBuffer keysBuffer, VkDeviceSize keysOffset, uint32_t shift,
+                                VkBuffer keysBuffer, VkDeviceSize keysOffset, uint32_t shift, uint32_t digitBits,
                                 uint32_t prefixCount, VkBuffer prefixesBuffer, VkDeviceSize prefixesOffset,
                                 VkBuffer histogramBuffer, VkDeviceSize histogramOffset) {
   if (!sorter) return;
+  const size_t smem = (size_t)prefixCount * ((size_t)1 << (digitBits & 31)) * sizeof(uint32_t);
   if (!keysBuffer || !histogramBuffer || prefixCount == 0 || prefixCount > (uint32_t)kDistMaxSplitters ||
-      shift > 24 || (shift & 7u) || (!prefixesBuffer && shift < 24)) {
+      digitBits == 0 || digitBits > 12 || shift + digitBits > 32 || smem > 160 * 1024 ||
+      (!prefixesBuffer && shift + digitBits < 32)) {
     NoteError(sorter, cudaErrorInvalidValue);
     return;
   }
@@ -699,23 +701,30 @@ void vrdxDistCmdPrefixHistogram(VkCommandBuffer commandBuffer, VrdxSorter sorter
   const uint32_t* keys = reinterpret_cast<const uint32_t*>(reinterpret_cast<char*>(keysBuffer) + keysOffset);
   const uint32_t* prefixes =
       prefixesBuffer ? reinterpret_cast<const uint32_t*>(reinterpret_cast<char*>(prefixesBuffer) + prefixesOffset)
-                     : reinterpret_cast<const uint32_t*>(keys);  // never read when shift == 24
+                     : reinterpret_cast<const uint32_t*>(keys);  // never read when the prefix is empty
   uint32_t* hist = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(histogramBuffer) + histogramOffset);
+  static std::atomic<bool> prepared{false};
+  if (!prepared.exchange(true))
+    NoteError(sorter, cudaFuncSetAttribute(DistPrefixHistogramKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           160 * 1024));
   const uint64_t vec_blocks = CeilDiv((uint64_t)elementCount / 4 + 1, (uint64_t)kDistHistThreads);
-  const uint64_t cap = (uint64_t)sorter->sm_count * 4;
+  const uint64_t cap = (uint64_t)sorter->sm_count * (smem > 64 * 1024 ? 1 : 4);
   const uint32_t grid = (uint32_t)(vec_blocks < cap ? vec_blocks : cap);
-  DistPrefixHistogramKernel<<<grid, kDistHistThreads, prefixCount * kRadix * sizeof(uint32_t), stream>>>(
-      keys, elementCount, shift, prefixCount, prefixes, hist);
+  DistPrefixHistogramKernel<<<grid, kDistHistThreads, smem, stream>>>(keys, elementCount, shift, digitBits,
+                                                                      prefixCount, prefixes, hist);
   NoteError(sorter, cudaGetLastError());
 }
 
-void vrdxDistCmdPartition(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t elementCount,
-                          VkBuffer keysBuffer, VkDeviceSize keysOffset, uint32_t splitterCount,
-                          VkBuffer splittersBuffer, VkDeviceSize splittersOffset, VkBuffer cursorsBuffer,
-                          VkDeviceSize cursorsOffset, VkBuffer outBuffer, VkDeviceSize outOffset) {
+namespace {
+void EnqueuePartition(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t elementCount, VkBuffer keysBuffer,
+                      VkDeviceSize keysOffset, uint32_t splitterCount, VkBuffer splittersBuffer,
+                      VkDeviceSize splittersOffset, VkBuffer cursorsBuffer, VkDeviceSize cursorsOffset,
+                      VkBuffer outBuffer, VkDeviceSize outOffset, uint32_t destCount, VkBuffer destTableBuffer,
+                      VkDeviceSize destTableOffset) {
   if (!sorter) return;
-  if (!keysBuffer || !outBuffer || !cursorsBuffer || splitterCount > (uint32_t)kDistMaxSplitters ||
-      (splitterCount && !splittersBuffer)) {
+  const bool scatter = destTableBuffer != nullptr;
+  if (!keysBuffer || (!scatter && !outBuffer) || !cursorsBuffer || splitterCount > (uint32_t)kDistMaxSplitters ||
+      (splitterCount && !splittersBuffer) || (scatter && (destCount == 0 || destCount > (uint32_t)kDistMaxDests))) {
     NoteError(sorter, cudaErrorInvalidValue);
     return;
   }
@@ -727,11 +736,90 @@ void vrdxDistCmdPartition(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint
       splittersBuffer ? reinterpret_cast<const uint32_t*>(reinterpret_cast<char*>(splittersBuffer) + splittersOffset)
                       : keys;  // never read when splitterCount == 0
   uint32_t* cursors = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(cursorsBuffer) + cursorsOffset);
-  uint32_t* out = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(outBuffer) + outOffset);
   const uint32_t grid = (uint32_t)CeilDiv((uint64_t)elementCount, (uint64_t)kDistPartTile);
-  DistPartitionKernel<<<grid, kDistPartThreads, 0, stream>>>(keys, elementCount, splitterCount, splitters,
-                                                             cursors, out);
+  if (scatter) {
+    const char* table = reinterpret_cast<const char*>(destTableBuffer) + destTableOffset;
+    const unsigned long long* ptrs = reinterpret_cast<const unsigned long long*>(table);
+    const uint32_t* first_pos = reinterpret_cast<const uint32_t*>(table + sizeof(unsigned long long) * destCount);
+    DistPartitionKernel<true><<<grid, kDistPartThreads, 0, stream>>>(keys, elementCount, splitterCount, splitters,
+                                                                     cursors, nullptr, destCount, ptrs, first_pos);
+  } else {
+    uint32_t* out = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(outBuffer) + outOffset);
+    DistPartitionKernel<false><<<grid, kDistPartThreads, 0, stream>>>(keys, elementCount, splitterCount, splitters,
+                                                                      cursors, out, 0, nullptr, nullptr);
+  }
   NoteError(sorter, cudaGetLastError());
+}
+}  // namespace
+
+void vrdxDistCmdPartition(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t elementCount,
+                          VkBuffer keysBuffer, VkDeviceSize keysOffset, uint32_t splitterCount,
+                          VkBuffer splittersBuffer, VkDeviceSize splittersOffset, VkBuffer cursorsBuffer,
+                          VkDeviceSize cursorsOffset, VkBuffer outBuffer, VkDeviceSize outOffset) {
+  EnqueuePartition(commandBuffer, sorter, elementCount, keysBuffer, keysOffset, splitterCount, splittersBuffer,
+                   splittersOffset, cursorsBuffer, cursorsOffset, outBuffer, outOffset, 0, nullptr, 0);
+}
+
+void vrdxDistCmdPartitionScatter(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t elementCount,
+                                 VkBuffer keysBuffer, VkDeviceSize keysOffset, uint32_t splitterCount,
+                                 VkBuffer splittersBuffer, VkDeviceSize splittersOffset, VkBuffer cursorsBuffer,
+                                 VkDeviceSize cursorsOffset, uint32_t destCount, VkBuffer destTableBuffer,
+                                 VkDeviceSize destTableOffset) {
+  if (sorter && !destTableBuffer) {
+    NoteError(sorter, cudaErrorInvalidValue);
+    return;
+  }
+  EnqueuePartition(commandBuffer, sorter, elementCount, keysBuffer, keysOffset, splitterCount, splittersBuffer,
+                   splittersOffset, cursorsBuffer, cursorsOffset, nullptr, 0, destCount, destTableBuffer,
+                   destTableOffset);
+}
+
+VkResult vrdxDistAllocShared(VkDevice device, VkDeviceSize size, VkBuffer* pBuffer,
+                             unsigned char handle[VRDX_DIST_IPC_HANDLE_BYTES]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == VRDX_DIST_IPC_HANDLE_BYTES, "IPC handle size");
+  if (!pBuffer || !handle || size == 0) return VK_ERROR_INITIALIZATION_FAILED;
+  DeviceGuard guard(DeviceFromHandle(device));
+  void* p = nullptr;
+  if (cudaMalloc(&p, size) != cudaSuccess) {
+    cudaGetLastError();
+    return VK_ERROR_OUT_OF_DEVICE_MEMORY;
+  }
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(p);
+    return VK_ERROR_FEATURE_NOT_PRESENT;
+  }
+  std::memcpy(handle, &h, sizeof(h));
+  *pBuffer = reinterpret_cast<VkBuffer>(p);
+  return VK_SUCCESS;
+}
+
+void vrdxDistFreeShared(VkDevice device, VkBuffer buffer) {
+  if (!buffer) return;
+  DeviceGuard guard(DeviceFromHandle(device));
+  cudaFree(reinterpret_cast<void*>(buffer));
+}
+
+VkResult vrdxDistOpenShared(VkDevice device, const unsigned char handle[VRDX_DIST_IPC_HANDLE_BYTES],
+                            VkBuffer* pBuffer) {
+  if (!pBuffer || !handle) return VK_ERROR_INITIALIZATION_FAILED;
+  DeviceGuard guard(DeviceFromHandle(device));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+    cudaGetLastError();
+    return VK_ERROR_INITIALIZATION_FAILED;
+  }
+  *pBuffer = reinterpret_cast<VkBuffer>(p);
+  return VK_SUCCESS;
+}
+
+void vrdxDistCloseShared(VkDevice device, VkBuffer buffer) {
+  if (!buffer) return;
+  DeviceGuard guard(DeviceFromHandle(device));
+  cudaIpcCloseMemHandle(reinterpret_cast<void*>(buffer));
 }
 
 }  // extern "C"

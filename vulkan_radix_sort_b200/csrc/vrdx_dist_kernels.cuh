@@ -23,20 +23,22 @@ struct DistPrefixes {
 constexpr int kDistHistThreads = 512;
 
 __global__ void __launch_bounds__(kDistHistThreads)
-DistPrefixHistogramKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t shift, uint32_t prefix_count,
-                          const uint32_t* __restrict__ prefixes, uint32_t* __restrict__ hist) {
-  extern __shared__ uint32_t sh[];  // [prefix_count][256]
+DistPrefixHistogramKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t shift, uint32_t digit_bits,
+                          uint32_t prefix_count, const uint32_t* __restrict__ prefixes, uint32_t* __restrict__ hist) {
+  extern __shared__ uint32_t sh[];  // [prefix_count][2^digit_bits]
   __shared__ uint32_t s_prefix[kDistMaxSplitters];
   const int tid = threadIdx.x;
-  for (uint32_t i = tid; i < prefix_count * kRadix; i += kDistHistThreads) sh[i] = 0;
+  const uint32_t bins = 1u << digit_bits;
+  for (uint32_t i = tid; i < prefix_count * bins; i += kDistHistThreads) sh[i] = 0;
   if (tid < (int)prefix_count) s_prefix[tid] = prefixes[tid];
   __syncthreads();
-  const bool top = shift >= 24;  // no bits above the digit: every key matches
+  const bool top = shift + digit_bits >= 32;  // no bits above the digit: every key matches
+  const uint32_t dmask = bins - 1u;
   auto count_key = [&](uint32_t k) {
-    const uint32_t d = (k >> shift) & 0xFFu;
-    const uint32_t hi = top ? 0u : (k >> (shift + 8));
+    const uint32_t d = (k >> shift) & dmask;
+    const uint32_t hi = top ? 0u : (k >> (shift + digit_bits));
     for (uint32_t j = 0; j < prefix_count; ++j)
-      if (top || hi == s_prefix[j]) atomicAdd(&sh[j * kRadix + d], 1u);
+      if (top || hi == s_prefix[j]) atomicAdd(&sh[j * bins + d], 1u);
   };
   const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(keys) >> 2) & 3u);
   uint32_t head = mis ? 4u - mis : 0u;
@@ -55,7 +57,7 @@ DistPrefixHistogramKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_
     if (tid < 4 && t < n) count_key(keys[t]);
   }
   __syncthreads();
-  for (uint32_t i = tid; i < prefix_count * kRadix; i += kDistHistThreads) {
+  for (uint32_t i = tid; i < prefix_count * bins; i += kDistHistThreads) {
     const uint32_t c = sh[i];
     if (c) atomicAdd(hist + i, c);
   }
@@ -71,19 +73,36 @@ constexpr int kDistPartItems = 16;
 constexpr int kDistPartTile = kDistPartThreads * kDistPartItems;
 constexpr int kDistClassSlots = 32;  // classes padded to a power of two
 
+// SCATTER = false: out[p] = key (class-ordered local buffer).
+// SCATTER = true : dest_ptr[j][p - first_pos[j]] = key for the destination j that owns position p —
+//                  the exchange is fused into the partition; the stores go to peer memory over NVLink.
+constexpr int kDistMaxDests = kDistMaxSplitters + 1;
+struct DistDestTable {
+  unsigned long long ptr[kDistMaxDests];
+  uint32_t first_pos[kDistMaxDests + 1];
+};
+
+template <bool SCATTER>
 __global__ void __launch_bounds__(kDistPartThreads)
 DistPartitionKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t splitter_count,
                     const uint32_t* __restrict__ splitters, uint32_t* __restrict__ cursors,
-                    uint32_t* __restrict__ out) {
+                    uint32_t* __restrict__ out, uint32_t dest_count,
+                    const unsigned long long* __restrict__ dest_ptrs, const uint32_t* __restrict__ first_pos) {
   constexpr int kWarps = kDistPartThreads / 32;
   __shared__ uint32_t s_u[kDistMaxSplitters];
   __shared__ uint32_t s_cnt[kWarps][kDistClassSlots];  // per-warp class counts, later slot bases
   __shared__ uint32_t s_base[kDistClassSlots];         // tile-local first slot of each class
   __shared__ uint32_t s_gbase[kDistClassSlots];        // global slot of tile-local slot 0, per class
   __shared__ uint32_t s_keys[kDistPartTile];
+  __shared__ unsigned long long s_dptr[kDistMaxDests];
+  __shared__ uint32_t s_dpos[kDistMaxDests + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t tile_start = (uint64_t)blockIdx.x * kDistPartTile;
   if (tile_start >= n) return;
+  if (SCATTER) {
+    if (tid < (int)dest_count) s_dptr[tid] = dest_ptrs[tid];
+    if (tid <= (int)dest_count) s_dpos[tid] = first_pos[tid];
+  }
   const uint32_t remaining = (uint32_t)(n - tile_start);
   const uint32_t tile_count = remaining < (uint32_t)kDistPartTile ? remaining : (uint32_t)kDistPartTile;
   if (tid < (int)splitter_count) s_u[tid] = splitters[tid];
@@ -158,7 +177,14 @@ DistPartitionKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t spli
         gt += k > s_u[j];
         eq |= k == s_u[j];
       }
-      out[s_gbase[2u * gt + eq] + slot] = k;
+      const uint32_t p = s_gbase[2u * gt + eq] + slot;  // class-ordered position among the local keys
+      if (!SCATTER) {
+        out[p] = k;
+      } else {
+        uint32_t j = 0;
+        for (uint32_t d = 1; d < dest_count; ++d) j += p >= s_dpos[d];
+        reinterpret_cast<uint32_t*>(s_dptr[j])[p - s_dpos[j]] = k;
+      }
     }
   }
 }

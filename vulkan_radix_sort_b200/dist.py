@@ -11,7 +11,11 @@ BASELINE.json configs[4] / SURVEY.md §8(e).  The reference is single-device; th
   2. local multi-split (vrdxDistCmdPartition) into <= 2G-1 classes (open intervals between
      splitters and one tie class per distinct splitter value), class-ordered, so the keys bound
      for each destination rank are ONE contiguous slice of the output;
-  3. all-to-all-v of those slices (NCCL grouped send/recv over NVLink / NVSwitch);
+  3. exchange.  Default on GPUs: FUSED into the multi-split — vrdxDistCmdPartitionScatter stores
+     every key straight into its destination rank's receive buffer (peer memory mapped over CUDA
+     IPC), so the data crosses NVLink / NVSwitch while the kernel is still ranking other tiles and
+     no separate collective runs; one tiny all-reduce acts as the barrier before the local sort.
+     Baseline / CPU path: an all-to-all-v of the contiguous slices (NCCL grouped send/recv, gloo);
   4. local LSD sort of what arrived (vrdxCmdSort through the C-ABI).
 
 Afterwards rank r holds the keys of global ranks [T_r, T_{r+1}) in ascending order, so the
@@ -27,7 +31,10 @@ from dataclasses import dataclass
 import torch
 import torch.distributed as dist
 
-LEVEL_SHIFTS = (24, 16, 8, 0)
+def search_levels(boundaries: int):
+    """(shift, bits) of each level of the splitter search: 8/12/12 bits while the per-prefix
+    histograms fit in shared memory (<= 7 boundaries), else four 8-bit levels."""
+    return ((24, 8), (12, 12), (0, 12)) if boundaries <= 7 else ((24, 8), (16, 8), (8, 8), (0, 8))
 
 
 def _u32_as_i32(t: torch.Tensor) -> torch.Tensor:
@@ -51,16 +58,33 @@ class CudaBackend:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def prefix_histogram(self, keys: torch.Tensor, count: int, shift: int, prefixes: torch.Tensor) -> torch.Tensor:
-        """-> int64 [P, 256]: local digit histogram at `shift` of the keys matching each prefix."""
+    def prefix_histogram(self, keys: torch.Tensor, count: int, shift: int, bits: int, prefixes: torch.Tensor) -> torch.Tensor:
+        """-> int64 [P, 2^bits]: local digit histogram at `shift` of the keys matching each prefix."""
         p = int(prefixes.numel())
-        hist = torch.zeros(p * 256, dtype=torch.int32, device=self.device)
+        hist = torch.zeros(p << bits, dtype=torch.int32, device=self.device)
         pref32 = _u32_as_i32(prefixes)
         self.api.load_library().vrdxDistCmdPrefixHistogram(
-            self._stream(), self.sorter.handle, count, keys.data_ptr(), 0, shift, p, pref32.data_ptr(), 0,
+            self._stream(), self.sorter.handle, count, keys.data_ptr(), 0, shift, bits, p, pref32.data_ptr(), 0,
             hist.data_ptr(), 0)
         self.sorter.check()
-        return (hist.to(torch.int64) & 0xFFFFFFFF).view(p, 256)
+        return (hist.to(torch.int64) & 0xFFFFFFFF).view(p, 1 << bits)
+
+    def partition_scatter(self, keys: torch.Tensor, count: int, splitters: torch.Tensor, class_starts: torch.Tensor,
+                          dest_ptrs, first_pos) -> None:
+        """Fused partition + exchange: keys go straight into the peers' receive buffers."""
+        m = int(splitters.numel())
+        spl = _u32_as_i32(splitters) if m else None
+        cursors = _u32_as_i32(class_starts)
+        g = len(dest_ptrs)
+        table = torch.empty(8 * g + 4 * (g + 1), dtype=torch.uint8)
+        table[:8 * g] = torch.tensor([int(x) for x in dest_ptrs], dtype=torch.int64).view(torch.uint8)
+        table[8 * g:] = torch.tensor([int(x) for x in first_pos], dtype=torch.int64).to(torch.int32).view(torch.uint8)
+        table_d = table.to(self.device)
+        self.api.load_library().vrdxDistCmdPartitionScatter(
+            self._stream(), self.sorter.handle, count, keys.data_ptr(), 0, m, spl.data_ptr() if m else None, 0,
+            cursors.data_ptr(), 0, g, table_d.data_ptr(), 0)
+        self.sorter.check()
+        self._keepalive = (spl, cursors, table_d)
 
     def partition(self, keys: torch.Tensor, count: int, splitters: torch.Tensor, class_starts: torch.Tensor,
                   out: torch.Tensor) -> None:
@@ -82,6 +106,61 @@ class CudaBackend:
         self.sorter.close()
 
 
+class _RawCudaArray:
+    """__cuda_array_interface__ view of raw device memory, so torch can wrap it without owning it."""
+
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<i4", "data": (ptr, False), "version": 3}
+
+
+class SharedReceive:
+    """This rank's receive buffer, allocated so that every other rank on the node can map it
+    (cudaMalloc + CUDA IPC), plus the mapped addresses of all peers' buffers."""
+
+    def __init__(self, backend: CudaBackend, capacity: int, group=None):
+        import ctypes
+        self.api = backend.api
+        self.lib = backend.api.load_library()
+        self.device = backend.device
+        self.capacity = int(capacity)
+        self.group = group
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = backend.api.cuda_device(self.device.index)
+        self._dev = dev
+        own = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        res = self.lib.vrdxDistAllocShared(dev, 4 * self.capacity, ctypes.byref(own), handle)
+        if res != backend.api.VK_SUCCESS:
+            raise RuntimeError(f"vrdxDistAllocShared failed: VkResult {res}")
+        self.own_ptr = own.value
+        mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).to(self.device)
+        everyone = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(everyone, mine, group=group)
+        self.peer_ptrs, self._opened = [], []
+        for r, h in enumerate(everyone):
+            if r == rank:
+                self.peer_ptrs.append(self.own_ptr)
+                continue
+            p = ctypes.c_void_p()
+            res = self.lib.vrdxDistOpenShared(dev, bytes(h.cpu().numpy().tobytes()), ctypes.byref(p))
+            if res != backend.api.VK_SUCCESS:
+                raise RuntimeError(f"vrdxDistOpenShared(rank {r}) failed: VkResult {res}")
+            self.peer_ptrs.append(p.value)
+            self._opened.append(p.value)
+        self.tensor = torch.as_tensor(_RawCudaArray(self.own_ptr, self.capacity), device=self.device)
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)  # nobody may still be storing into a buffer that is about to be freed
+        for p in self._opened:
+            self.lib.vrdxDistCloseShared(self._dev, p)
+        self._opened = []
+        if self.own_ptr:
+            self.tensor = None
+            self.lib.vrdxDistFreeShared(self._dev, self.own_ptr)
+            self.own_ptr = None
+
+
 # ------------------------------------------------------------------------------ host logic
 
 @dataclass
@@ -100,7 +179,7 @@ def _as_u32_tensor(values, device):
 
 
 def find_splitters(backend, keys: torch.Tensor, count: int, group=None):
-    """The 4-level search.  Returns per boundary k=1..G-1 (tensors on keys.device, int64):
+    """The multi-level search (search_levels).  Returns per boundary k=1..G-1 (tensors on keys.device, int64):
     value v_k, global #keys < v_k, global #keys == v_k, local #keys < v_k, local #keys == v_k;
     plus N and the targets T_k."""
     world = dist.get_world_size(group)
@@ -119,23 +198,23 @@ def find_splitters(backend, keys: torch.Tensor, count: int, group=None):
     less_g = torch.zeros(nb, dtype=torch.int64, device=device)
     less_l = torch.zeros(nb, dtype=torch.int64, device=device)
     eq_g = eq_l = None
-    for level, shift in enumerate(LEVEL_SHIFTS):
+    for level, (shift, bits) in enumerate(search_levels(nb)):
         if level == 0:
-            h_local = backend.prefix_histogram(keys, count, shift, prefix[:1]).expand(nb, 256)
+            h_local = backend.prefix_histogram(keys, count, shift, bits, prefix[:1]).expand(nb, 1 << bits)
         else:
-            h_local = backend.prefix_histogram(keys, count, shift, prefix)
+            h_local = backend.prefix_histogram(keys, count, shift, bits, prefix)
         h_global = h_local.clone().contiguous()
         dist.all_reduce(h_global, group=group)
         cum = torch.cumsum(h_global, dim=1)                       # inclusive
         digit = (cum <= remaining[:, None]).sum(dim=1)            # first digit whose cumulative count exceeds the target rank
-        digit = digit.clamp(max=255)
+        digit = digit.clamp(max=(1 << bits) - 1)
         excl_g = torch.where(digit > 0, cum.gather(1, (digit - 1).clamp(min=0)[:, None])[:, 0], torch.zeros_like(remaining))
         cum_l = torch.cumsum(h_local, dim=1)
         excl_l = torch.where(digit > 0, cum_l.gather(1, (digit - 1).clamp(min=0)[:, None])[:, 0], torch.zeros_like(remaining))
         less_g = less_g + excl_g
         less_l = less_l + excl_l
         remaining = remaining - excl_g
-        prefix = prefix * 256 + digit
+        prefix = prefix * (1 << bits) + digit
         eq_g = h_global.gather(1, digit[:, None])[:, 0]
         eq_l = h_local.gather(1, digit[:, None])[:, 0]
     return prefix, less_g, eq_g, less_l, eq_l, total, targets
@@ -180,9 +259,13 @@ def make_plan(backend, keys: torch.Tensor, count: int, group=None) -> SplitPlan:
 
 
 def distributed_sort(backend, keys: torch.Tensor, count: int | None = None, group=None, recv: torch.Tensor | None = None,
-                     part: torch.Tensor | None = None, storage: torch.Tensor | None = None, timers=None):
-    """Sort the union of every rank's keys[0:count].  Returns (recv_buffer, recv_count): rank r's
-    slice of the globally sorted sequence (global ranks [T_r, T_{r+1}))."""
+                     part: torch.Tensor | None = None, storage: torch.Tensor | None = None, timers=None,
+                     shared: "SharedReceive | None" = None):
+    """Sort the union of every rank's keys[0:count].  Returns (recv_buffer, recv_count, plan): rank
+    r's slice of the globally sorted sequence (global ranks [T_r, T_{r+1})).
+
+    With ``shared`` (a SharedReceive) the exchange is fused into the partition kernel (peer stores
+    over NVLink); otherwise the keys are multi-split locally and exchanged with an all-to-all-v."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     n = int(keys.numel() if count is None else count)
@@ -198,18 +281,36 @@ def distributed_sort(backend, keys: torch.Tensor, count: int | None = None, grou
     in_splits = plan.sizes[rank]
     out_splits = [plan.sizes[s][rank] for s in range(world)]
     recv_count = sum(out_splits)
-    if part is None:
-        part = torch.empty(max(n, 1), dtype=keys.dtype, device=device)
-    if recv is None or recv.numel() < recv_count:
-        recv = torch.empty(max(recv_count, 1), dtype=keys.dtype, device=device)
-    if n:
-        backend.partition(keys, n, _as_u32_tensor(plan.distinct, device), _as_u32_tensor(plan.class_starts, device), part)
-    mark("partition")
-    if world > 1:
-        dist.all_to_all_single(recv[:recv_count], part[:n], out_splits, in_splits, group=group)
+    splitters_t = _as_u32_tensor(plan.distinct, device)
+    starts_t = _as_u32_tensor(plan.class_starts, device)
+    if shared is not None:
+        if recv_count > shared.capacity:
+            raise RuntimeError(f"receive buffer too small: {recv_count} > {shared.capacity}")
+        recv = shared.tensor
+        # where my keys for destination j start inside j's buffer: after the keys of lower ranks
+        first_pos = [0]
+        for j in range(world):
+            first_pos.append(first_pos[-1] + in_splits[j])
+        dest_ptrs = [shared.peer_ptrs[j] + 4 * sum(plan.sizes[s][j] for s in range(rank)) for j in range(world)]
+        if n:
+            backend.partition_scatter(keys, n, splitters_t, starts_t, dest_ptrs, first_pos)
+        mark("partition")
+        token = torch.zeros(1, dtype=torch.int32, device=device)
+        dist.all_reduce(token, group=group)      # barrier on the stream: every rank's stores have completed
+        mark("exchange")
     else:
-        recv[:recv_count].copy_(part[:n])
-    mark("exchange")
+        if part is None:
+            part = torch.empty(max(n, 1), dtype=keys.dtype, device=device)
+        if recv is None or recv.numel() < recv_count:
+            recv = torch.empty(max(recv_count, 1), dtype=keys.dtype, device=device)
+        if n:
+            backend.partition(keys, n, splitters_t, starts_t, part)
+        mark("partition")
+        if world > 1:
+            dist.all_to_all_single(recv[:recv_count], part[:n], out_splits, in_splits, group=group)
+        else:
+            recv[:recv_count].copy_(part[:n])
+        mark("exchange")
     if recv_count:
         backend.local_sort(recv, recv_count, storage)
     mark("local_sort")
