@@ -46,10 +46,22 @@ DistPrefixHistogramKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_
   const uint4* __restrict__ body = reinterpret_cast<const uint4*>(keys + head);
   const uint64_t nvec = (uint64_t)(n - head) >> 2;
   const uint32_t tail_start = head + (uint32_t)(nvec << 2);
-  for (uint64_t v = (uint64_t)blockIdx.x * kDistHistThreads + tid; v < nvec;
-       v += (uint64_t)gridDim.x * kDistHistThreads) {
-    const uint4 q = __ldcs(body + v);
-    count_key(q.x); count_key(q.y); count_key(q.z); count_key(q.w);
+  // four 128-bit loads in flight per thread: the large-histogram configurations run one CTA per SM
+  constexpr int kUnroll = 4;
+  const uint64_t stride = (uint64_t)gridDim.x * kDistHistThreads;
+  for (uint64_t v0 = (uint64_t)blockIdx.x * kDistHistThreads + tid; v0 < nvec; v0 += stride * kUnroll) {
+    uint4 q[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint64_t v = v0 + (uint64_t)u * stride;
+      q[u] = v < nvec ? __ldcs(body + v) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      if (v0 + (uint64_t)u * stride < nvec) {
+        count_key(q[u].x); count_key(q[u].y); count_key(q[u].z); count_key(q[u].w);
+      }
+    }
   }
   if (blockIdx.x == 0) {
     if ((uint32_t)tid < head) count_key(keys[tid]);

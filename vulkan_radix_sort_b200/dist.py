@@ -179,45 +179,47 @@ def _as_u32_tensor(values, device):
 
 
 def find_splitters(backend, keys: torch.Tensor, count: int, group=None):
-    """The multi-level search (search_levels).  Returns per boundary k=1..G-1 (tensors on keys.device, int64):
+    """The multi-level search (search_levels).  Returns, per boundary k = 1..G-1, Python lists:
     value v_k, global #keys < v_k, global #keys == v_k, local #keys < v_k, local #keys == v_k;
-    plus N and the targets T_k."""
+    plus N and the targets T_k.  The histograms are reduced across ranks on the device
+    (all-reduce); the few hundred bins of arithmetic per level run on the host."""
+    import numpy as np
     world = dist.get_world_size(group)
     device = keys.device
-    n_local = torch.tensor([count], dtype=torch.int64, device=device)
-    n_total_t = n_local.clone()
+    n_total_t = torch.tensor([count], dtype=torch.int64, device=device)
     dist.all_reduce(n_total_t, group=group)
     total = int(n_total_t.item())
     targets = [k * total // world for k in range(world + 1)]
     nb = world - 1
     if nb == 0 or total == 0:
-        z = torch.zeros(0, dtype=torch.int64, device=device)
-        return z, z, z, z, z, total, targets
-    remaining = torch.tensor(targets[1:world], dtype=torch.int64, device=device)  # rank of the wanted key inside the current bucket
-    prefix = torch.zeros(nb, dtype=torch.int64, device=device)
-    less_g = torch.zeros(nb, dtype=torch.int64, device=device)
-    less_l = torch.zeros(nb, dtype=torch.int64, device=device)
+        return [], [], [], [], [], total, targets
+    remaining = np.array(targets[1:world], dtype=np.int64)   # rank of the wanted key inside the current bucket
+    prefix = np.zeros(nb, dtype=np.int64)
+    less_g = np.zeros(nb, dtype=np.int64)
+    less_l = np.zeros(nb, dtype=np.int64)
     eq_g = eq_l = None
+    rows = np.arange(nb)
     for level, (shift, bits) in enumerate(search_levels(nb)):
-        if level == 0:
-            h_local = backend.prefix_histogram(keys, count, shift, bits, prefix[:1]).expand(nb, 1 << bits)
-        else:
-            h_local = backend.prefix_histogram(keys, count, shift, bits, prefix)
-        h_global = h_local.clone().contiguous()
-        dist.all_reduce(h_global, group=group)
-        cum = torch.cumsum(h_global, dim=1)                       # inclusive
-        digit = (cum <= remaining[:, None]).sum(dim=1)            # first digit whose cumulative count exceeds the target rank
-        digit = digit.clamp(max=(1 << bits) - 1)
-        excl_g = torch.where(digit > 0, cum.gather(1, (digit - 1).clamp(min=0)[:, None])[:, 0], torch.zeros_like(remaining))
-        cum_l = torch.cumsum(h_local, dim=1)
-        excl_l = torch.where(digit > 0, cum_l.gather(1, (digit - 1).clamp(min=0)[:, None])[:, 0], torch.zeros_like(remaining))
-        less_g = less_g + excl_g
-        less_l = less_l + excl_l
+        p = 1 if level == 0 else nb
+        h_local_t = backend.prefix_histogram(keys, count, shift, bits, torch.from_numpy(prefix[:p]).to(device))
+        both = torch.stack([h_local_t, h_local_t]).contiguous()          # [0] stays local, [1] is reduced
+        dist.all_reduce(both[1], group=group)
+        both_h = both.cpu().numpy()                                       # one small D2H per level
+        h_local = np.broadcast_to(both_h[0], (nb, 1 << bits)) if level == 0 else both_h[0]
+        h_global = np.broadcast_to(both_h[1], (nb, 1 << bits)) if level == 0 else both_h[1]
+        cum = np.cumsum(h_global, axis=1)                                 # inclusive
+        digit = np.minimum((cum <= remaining[:, None]).sum(axis=1), (1 << bits) - 1)
+        prev = np.maximum(digit - 1, 0)
+        excl_g = np.where(digit > 0, cum[rows, prev], 0)
+        excl_l = np.where(digit > 0, np.cumsum(h_local, axis=1)[rows, prev], 0)
+        less_g += excl_g
+        less_l += excl_l
         remaining = remaining - excl_g
         prefix = prefix * (1 << bits) + digit
-        eq_g = h_global.gather(1, digit[:, None])[:, 0]
-        eq_l = h_local.gather(1, digit[:, None])[:, 0]
-    return prefix, less_g, eq_g, less_l, eq_l, total, targets
+        eq_g = h_global[rows, digit]
+        eq_l = h_local[rows, digit]
+    as_list = lambda a: [int(x) for x in a]
+    return as_list(prefix), as_list(less_g), as_list(eq_g), as_list(less_l), as_list(eq_l), total, targets
 
 
 def make_plan(backend, keys: torch.Tensor, count: int, group=None) -> SplitPlan:
@@ -226,11 +228,11 @@ def make_plan(backend, keys: torch.Tensor, count: int, group=None) -> SplitPlan:
     v, less_g, eq_g, less_l, eq_l, total, targets = find_splitters(backend, keys, count, group)
     nb = world - 1
     # every rank's local statistics: [count, less_l(1..nb), eq_l(1..nb)]
-    mine = torch.cat([torch.tensor([count], dtype=torch.int64, device=keys.device), less_l, eq_l]).contiguous()
+    mine = torch.tensor([count] + less_l + eq_l, dtype=torch.int64, device=keys.device)
     everyone = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(everyone, mine, group=group)
-    stats = torch.stack(everyone).cpu().tolist()                 # the one host synchronisation of the plan
-    v_h, less_g_h = v.cpu().tolist(), less_g.cpu().tolist()
+    stats = torch.stack(everyone).cpu().tolist()
+    v_h, less_g_h = v, less_g
     counts = [int(r[0]) for r in stats]
     less_l_all = [[int(x) for x in r[1:1 + nb]] for r in stats]
     eq_l_all = [[int(x) for x in r[1 + nb:1 + 2 * nb]] for r in stats]
