@@ -708,7 +708,7 @@ void vrdxDistCmdPrefixHistogram(VkCommandBuffer commandBuffer, VrdxSorter sorter
     NoteError(sorter, cudaFuncSetAttribute(DistPrefixHistogramKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            160 * 1024));
   const uint64_t vec_blocks = CeilDiv((uint64_t)elementCount / 4 + 1, (uint64_t)kDistHistThreads);
-  const uint64_t cap = (uint64_t)sorter->sm_count * (smem > 64 * 1024 ? 1 : 4);
+  const uint64_t cap = (uint64_t)sorter->sm_count * (smem > 112 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4));
   const uint32_t grid = (uint32_t)(vec_blocks < cap ? vec_blocks : cap);
   DistPrefixHistogramKernel<<<grid, kDistHistThreads, smem, stream>>>(keys, elementCount, shift, digitBits,
                                                                       prefixCount, prefixes, hist);

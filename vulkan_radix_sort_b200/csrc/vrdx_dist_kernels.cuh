@@ -27,18 +27,41 @@ DistPrefixHistogramKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_
                           uint32_t prefix_count, const uint32_t* __restrict__ prefixes, uint32_t* __restrict__ hist) {
   extern __shared__ uint32_t sh[];  // [prefix_count][2^digit_bits]
   __shared__ uint32_t s_prefix[kDistMaxSplitters];
+  __shared__ uint32_t s_cand[kRadix];  // per top byte: bit j set if prefix j can match a key with that top byte
   const int tid = threadIdx.x;
   const uint32_t bins = 1u << digit_bits;
+  const uint32_t hi_shift = shift + digit_bits;  // bits above the digit
+  const bool top = hi_shift >= 32;               // no bits above the digit: every key matches
   for (uint32_t i = tid; i < prefix_count * bins; i += kDistHistThreads) sh[i] = 0;
   if (tid < (int)prefix_count) s_prefix[tid] = prefixes[tid];
+  if (tid < kRadix) {
+    uint32_t m = 0;
+    if (!top) {
+      for (uint32_t j = 0; j < prefix_count; ++j) {
+        const uint32_t p = prefixes[j];
+        // top byte(s) of the keys matching prefix j: the prefix holds (32 - hi_shift) bits
+        const uint32_t pbits = 32 - hi_shift;
+        const bool hit = pbits >= 8 ? ((p >> (pbits - 8)) == (uint32_t)tid) : (((uint32_t)tid >> (8 - pbits)) == p);
+        m |= hit ? (1u << j) : 0u;
+      }
+    }
+    s_cand[tid] = m;
+  }
   __syncthreads();
-  const bool top = shift + digit_bits >= 32;  // no bits above the digit: every key matches
   const uint32_t dmask = bins - 1u;
   auto count_key = [&](uint32_t k) {
     const uint32_t d = (k >> shift) & dmask;
-    const uint32_t hi = top ? 0u : (k >> (shift + digit_bits));
-    for (uint32_t j = 0; j < prefix_count; ++j)
-      if (top || hi == s_prefix[j]) atomicAdd(&sh[j * bins + d], 1u);
+    if (top) {
+      atomicAdd(&sh[d], 1u);  // prefix_count == 1 at the first level
+      return;
+    }
+    uint32_t m = s_cand[k >> 24];  // ~(prefix_count / 256) of uniform keys get past this
+    const uint32_t hi = k >> hi_shift;
+    while (m) {
+      const uint32_t j = __ffs(m) - 1;
+      m &= m - 1;
+      if (hi == s_prefix[j]) atomicAdd(&sh[j * bins + d], 1u);
+    }
   };
   const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(keys) >> 2) & 3u);
   uint32_t head = mis ? 4u - mis : 0u;
@@ -106,6 +129,7 @@ DistPartitionKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t spli
   __shared__ uint32_t s_base[kDistClassSlots];         // tile-local first slot of each class
   __shared__ uint32_t s_gbase[kDistClassSlots];        // global slot of tile-local slot 0, per class
   __shared__ uint32_t s_keys[kDistPartTile];
+  __shared__ uint32_t s_top[kRadix];
   __shared__ unsigned long long s_dptr[kDistMaxDests];
   __shared__ uint32_t s_dpos[kDistMaxDests + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -119,7 +143,29 @@ DistPartitionKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t spli
   const uint32_t tile_count = remaining < (uint32_t)kDistPartTile ? remaining : (uint32_t)kDistPartTile;
   if (tid < (int)splitter_count) s_u[tid] = splitters[tid];
   if (lane < kDistClassSlots) s_cnt[warp][lane] = 0;
+  {
+    // per top byte b: if no splitter has top byte b, every key with that byte has the same class
+    // (2 * #splitters below it); otherwise the key needs the full comparison (flag in bit 31)
+    const uint32_t b = tid;  // kDistPartThreads == 256
+    uint32_t below = 0, inside = 0;
+    for (uint32_t j = 0; j < splitter_count; ++j) {
+      const uint32_t ub = splitters[j] >> 24;
+      below += ub < b;
+      inside |= ub == b;
+    }
+    s_top[b] = inside ? 0x80000000u : 2u * below;
+  }
   __syncthreads();
+  auto class_of = [&](uint32_t k) -> uint32_t {
+    const uint32_t t = s_top[k >> 24];
+    if (!(t & 0x80000000u)) return t;
+    uint32_t gt = 0, eq = 0;
+    for (uint32_t j = 0; j < splitter_count; ++j) {
+      gt += k > s_u[j];
+      eq |= k == s_u[j];
+    }
+    return 2u * gt + eq;
+  };
 
   const uint32_t lt = LaneMaskLt();
   const uint32_t woff = warp * 32 * kDistPartItems + lane;
@@ -132,13 +178,8 @@ DistPartitionKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t spli
 #pragma unroll
   for (int i = 0; i < kDistPartItems; ++i) {
     const bool valid = woff + 32 * i < tile_count;
-    uint32_t gt = 0, eq = 0;
-    for (uint32_t j = 0; j < splitter_count; ++j) {
-      gt += key[i] > s_u[j];
-      eq |= key[i] == s_u[j];
-    }
     // invalid (pad) lanes take the unused top slot so that they rank after every real key
-    const uint32_t c = valid ? 2u * gt + eq : (uint32_t)(kDistClassSlots - 1);
+    const uint32_t c = valid ? class_of(key[i]) : (uint32_t)(kDistClassSlots - 1);
     cls[i] = (uint8_t)c;
     uint32_t peers = 0xffffffffu;
 #pragma unroll
@@ -184,12 +225,7 @@ DistPartitionKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t spli
     const uint32_t slot = i * kDistPartThreads + tid;
     if (slot < tile_count) {
       const uint32_t k = s_keys[slot];
-      uint32_t gt = 0, eq = 0;
-      for (uint32_t j = 0; j < splitter_count; ++j) {
-        gt += k > s_u[j];
-        eq |= k == s_u[j];
-      }
-      const uint32_t p = s_gbase[2u * gt + eq] + slot;  // class-ordered position among the local keys
+      const uint32_t p = s_gbase[class_of(k)] + slot;  // class-ordered position among the local keys
       if (!SCATTER) {
         out[p] = k;
       } else {
