@@ -258,7 +258,7 @@ def run_single(args):
     # roofline of the dominant kernel (one onesweep pass): algorithmic 8 B/key per launch
     pass_gbs = PASS_BYTES_PER_KEY_KEYS * n / (pass_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": pass_gbs, "peak": peak, "unit": "GB/s", "frac": pass_gbs / peak,
-                "traffic": ncu_traffic_per_launch("keys_pass", n), "kernel": "OnesweepKernel (one LSD pass, keys-only)",
+                "traffic": ncu_traffic_per_launch("keys_pass", n), "kernel": "OnesweepKernel<.., MODE 1> (scatter pass of one LSD pass, keys-only)",
                 "algorithmic_bytes_per_launch": PASS_BYTES_PER_KEY_KEYS * n, "kernel_ms": pass_ms,
                 "peak_source": peak_src,
                 "whole_sort": {"bytes_per_key": BYTES_PER_KEY_KEYS,
@@ -292,6 +292,23 @@ def run_single(args):
     except torch.cuda.OutOfMemoryError as e:  # pragma: no cover
         extra["error"] = str(e)
 
+    # comparison point named by BASELINE.json: CUB Onesweep on the same box, through the reference's
+    # bench protocol (bench_cpp/bench cuda).  Comparison only — CUB is not in libvrdx_b200.so.
+    try:
+        exe = os.path.join(ROOT, "bench_cpp", "bench")
+        if os.path.exists(exe) and log2n >= 25 and not args.no_cub:
+            torch.cuda.empty_cache()
+            out = subprocess.run([exe, "cuda", "--sizes", f"2^{log2n}", "--seed", "1", "--runs", "3", "--no-verify",
+                                  "-o", "/tmp/vrdx_cub.csv"], capture_output=True, text=True, timeout=240)
+            for ln in open("/tmp/vrdx_cub.csv"):
+                f = ln.strip().split(",")
+                if len(f) == 7 and f[0] == "cuda":
+                    extra["cub_onesweep_%s_2^%d" % ("keys_only" if f[2] == "keys" else "key_value", log2n)] = {
+                        "value": float(f[5]), "unit": UNIT, "gpu_ms": float(f[3]),
+                        "note": "cub::DeviceRadixSort via bench_cpp (fresh data per run, median of 3)"}
+    except Exception as e:  # pragma: no cover
+        extra["cub_error"] = str(e)
+
     # CPU baseline: the reference's own CpuBenchmark::Sort on a bounded sample (rank 0, N=1 only)
     cpu = None
     try:
@@ -315,7 +332,8 @@ def run_single(args):
         "config": {"workload": f"32-bit keys-only, N=2^{log2n} uniform random (DataGenerator seed 1), vrdxCmdSort direct",
                    "l2": "inputs (1 GiB) larger than L2; a restore copy of the unsorted keys runs between timed steps",
                    "timing": "CUDA events on the launching stream around each sort; mean of K steps",
-                   "algorithm": "histogram + 4x onesweep (decoupled look-back), 8-bit digits"},
+                   "algorithm": "AUTO: reduce-then-scan at this N (per pass: chunked upsweep, 2 spine kernels, "
+                                "look-back-free scatter), 8-bit digits x 4 passes; onesweep below 3*2^23 keys"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_per_step,
                 "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": 4 * n,
                 "path": "pinned host keys -> cudaMemcpyAsync H2D -> vrdxCmdSort (C-ABI) -> cudaMemcpyAsync D2H"},
@@ -343,6 +361,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=28, help="developer override of the N=1 workload size")
     ap.add_argument("--log2n-per-gpu", type=int, default=29, help="developer override of the N>1 per-GPU size")
+    ap.add_argument("--no-cub", action="store_true", help="skip the CUB comparison run")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
