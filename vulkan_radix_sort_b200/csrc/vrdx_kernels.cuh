@@ -767,7 +767,7 @@ SpineReduceKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint
   const uint32_t r0 = blockIdx.x * rows_per;
   const uint32_t r1 = r0 + rows_per < chunks ? r0 + rows_per : chunks;
   uint32_t sum = 0;
-#pragma unroll 8
+#pragma unroll 16
   for (uint32_t r = r0; r < r1; ++r) sum += chunk_sums[(size_t)r * kRadix + tid];
   seg[(size_t)blockIdx.x * kRadix + tid] = sum;
   __threadfence();
@@ -810,11 +810,15 @@ SpineApplyKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint3
   const uint32_t r0 = blockIdx.x * rows_per;
   const uint32_t r1 = r0 + rows_per < chunks ? r0 + rows_per : chunks;
   uint32_t run = seg[(size_t)blockIdx.x * kRadix + tid];
-#pragma unroll 8
-  for (uint32_t r = r0; r < r1; ++r) {
-    const uint32_t v = chunk_sums[(size_t)r * kRadix + tid];
-    chunk_sums[(size_t)r * kRadix + tid] = run;
-    run += v;
+  for (uint32_t b0 = r0; b0 < r1; b0 += 16) {  // 16 rows in flight; loads never wait behind the aliasing stores
+    uint32_t v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = (b0 + j < r1) ? chunk_sums[(size_t)(b0 + j) * kRadix + tid] : 0u;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (b0 + j < r1) chunk_sums[(size_t)(b0 + j) * kRadix + tid] = run;
+      run += v[j];
+    }
   }
 }
 
