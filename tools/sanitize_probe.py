@@ -1,0 +1,26 @@
+"""Small sorts of every flavour for compute-sanitizer (memcheck / racecheck / synccheck)."""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vulkan_radix_sort_b200 import Sorter, api
+from vulkan_radix_sort_b200.datagen import make_keys
+flavours = {"onesweep": (1, 1, None), "rts": (2, 1, None), "onesweep_tma": (1, 2, None), "rts_tma": (2, 2, None),
+            "cluster4": (1, 1, (7, 7))}
+only = sys.argv[1:] or list(flavours)
+for name in only:
+    algo, load, res = flavours[name]
+    s = Sorter(0, algorithm=algo, tile_load=load, reserved=res)
+    for n in (1, 777, 6144, 20011, 70001):
+        for dist in ("uniform", "bits4"):
+            k = make_keys(dist, n, 3)
+            dk = torch.from_numpy(k.view(np.int32)).cuda()
+            dv = torch.arange(n, dtype=torch.int32, device="cuda")
+            cnt = torch.tensor([max(n - 5, 0)], dtype=torch.int32, device="cuda")
+            s.sort(dk.clone())
+            s.sort_key_value_indirect(dk, dv, cnt, max_count=n)
+            torch.cuda.synchronize()
+            c = int(cnt.item())
+            got = dk.cpu().numpy().view(np.uint32)
+            assert np.array_equal(got[:c], np.sort(k[:c], kind="stable")), (name, n, dist)
+    s.close()
+    print("ok", name, flush=True)

@@ -163,6 +163,8 @@ static const PassVariant kKeysVariants[] = {
     MakeClusterVariant<384, 16, false, 3, 4>(), MakeClusterVariant<384, 16, false, 3, 8>(),
     MakeVariant<256, 16, false, 6>(),           MakeVariant<256, 20, false, 4>(),
     MakeVariant<320, 16, false, 4>(),           MakeVariant<256, 24, false, 3>(),
+    MakeVariant<384, 16, false, 3, 16>(),       MakeVariant<256, 16, false, 4, 16>(),
+    MakeVariant<256, 8, false, 6, 16>(),        MakeVariant<256, 8, false, 6, 32>(),
 };
 static const PassVariant kPairVariants[] = {
     MakeVariant<384, 16, true, 3>(),            MakeVariant<256, 16, true, 5>(),
@@ -171,6 +173,8 @@ static const PassVariant kPairVariants[] = {
     MakeClusterVariant<384, 16, true, 3, 4>(),  MakeClusterVariant<384, 16, true, 3, 8>(),
     MakeVariant<256, 16, true, 6>(),            MakeVariant<256, 20, true, 4>(),
     MakeVariant<320, 16, true, 4>(),            MakeVariant<256, 24, true, 3>(),
+    MakeVariant<384, 16, true, 3, 16>(),        MakeVariant<256, 16, true, 4, 16>(),
+    MakeVariant<256, 8, true, 6, 16>(),         MakeVariant<256, 8, true, 6, 32>(),
 };
 constexpr int kDefaultKeysRtsVariant = 1;
 constexpr int kDefaultPairRtsVariant = 0;
@@ -187,7 +191,7 @@ constexpr int kNumPairVariants = sizeof(kPairVariants) / sizeof(kPairVariants[0]
 constexpr int kNumKeysTmaVariants = sizeof(kKeysTmaVariants) / sizeof(kKeysTmaVariants[0]);
 constexpr int kNumPairTmaVariants = sizeof(kPairTmaVariants) / sizeof(kPairTmaVariants[0]);
 // Smallest tile of any compiled variant: sizes the look-back buffers whichever variant runs.
-constexpr uint32_t kMinTile = 3072;  // 256 x 12
+constexpr uint32_t kMinTile = 2048;  // 256 x 8
 // AUTO: reduce-then-scan at and above this count, onesweep (fewer launches) below it.
 constexpr uint32_t kAutoRtsThreshold = 3u << 23;  // measured crossover between 2^24 and 2^25 (profiles/r01_sweep_n.txt)
 

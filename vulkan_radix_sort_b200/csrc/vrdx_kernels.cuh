@@ -149,11 +149,15 @@ HistogramKernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ 
   if (warp < kPasses) {
     uint32_t* h = gh + warp * kRadix + lane * 8;
     uint32_t c[8], sum = 0;
+    bool all_in_one = false;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { c[j] = __ldcg(h + j); sum += c[j]; }
+    for (int j = 0; j < 8; ++j) { c[j] = __ldcg(h + j); sum += c[j]; all_in_one |= (c[j] == n); }
     uint32_t excl = WarpInclusiveScan(sum, lane) - sum;
 #pragma unroll
     for (int j = 0; j < 8; ++j) { h[j] = excl; excl += c[j]; }
+    // one digit holds every key: this pass is the identity permutation (tiles will just copy)
+    const uint32_t any = __ballot_sync(0xffffffffu, all_in_one && n != 0);
+    if (lane == 0) hdr->pass_identity[warp] = any ? 1u : 0u;
   }
 }
 
@@ -345,6 +349,28 @@ OnesweepKernel(const PassArgs a) {
   const bool full = tile_count == (uint32_t)kTile;
 
   if (MODE != 1 && a.status_next != nullptr && tid < kRadix) a.status_next[(size_t)tile * kRadix + tid] = 0;
+
+  // ---- constant digit: a stable counting sort with one non-empty bucket is a copy --------------
+  if (a.hdr->pass_identity[a.pass]) {
+    const uint32_t* kin = a.keys_in + tile_start;
+    uint32_t* kout = a.keys_out + tile_start;
+    uint32_t ck[IPT], cv[KV ? IPT : 1];
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {  // all loads first: the stores below may alias them as far as the compiler knows
+      const uint32_t idx = i * THREADS + tid;
+      ck[i] = idx < tile_count ? LdStream(kin + idx) : 0u;
+      if (KV) cv[i] = idx < tile_count ? LdStream(a.vals_in + tile_start + idx) : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const uint32_t idx = i * THREADS + tid;
+      if (idx < tile_count) {
+        kout[idx] = ck[i];
+        if (KV) a.vals_out[tile_start + idx] = cv[i];
+      }
+    }
+    return;
+  }
 
   // ---- load: warp-striped, 128 B per warp-instruction -------------------------------------
   uint32_t key[IPT];
@@ -796,6 +822,9 @@ SpineReduceKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint
   for (int w = 0; w < kRadix / 32; ++w) prefix += (w < warp) ? s_warp[w] : 0u;
   hdr->global_hist[pass][tid] = prefix + incl - run;
   if (tid == 0 && pass == 0) hdr->element_count[0] = n;
+  // one digit holds every key: this pass is the identity permutation (the scatter tiles just copy)
+  const int any = __syncthreads_or(run == n && n != 0);
+  if (tid == 0) hdr->pass_identity[pass] = any ? 1u : 0u;
 }
 
 __global__ void __launch_bounds__(kRadix)

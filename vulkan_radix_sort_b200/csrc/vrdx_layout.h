@@ -28,8 +28,9 @@ struct alignas(16) StorageHeader {
   uint32_t element_count[4];             // slot 0: resolved element count (parity with the reference's count slot)
   uint32_t global_hist[kPasses][kRadix];  // digit histograms; exclusive-scanned in place by the histogram kernel
   uint32_t tickets[kPasses];              // dynamic tile ids, one counter per pass
-  uint32_t hist_blocks_done;              // last-block-done counter of the histogram kernel
+  uint32_t hist_blocks_done;              // last-block-done counter of the histogram / spine kernels
   uint32_t reserved[3];
+  uint32_t pass_identity[kPasses];        // 1: every key holds the same digit in this pass -> the pass is a copy
 };
 static_assert(sizeof(StorageHeader) % 16 == 0, "header must keep 16-byte alignment");
 
