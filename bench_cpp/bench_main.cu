@@ -186,6 +186,11 @@ class B200Benchmark : public BenchmarkBase {
     VrdxSorterCreateInfo info = {vrdxCudaPhysicalDevice(0), vrdxCudaDevice(0), VK_NULL_HANDLE};
     if (vrdxCreateSorter(&info, &sorter_) != VK_SUCCESS) { std::fprintf(stderr, "vrdxCreateSorter failed\n"); std::exit(2); }
     if (vrdxCudaCreateQueryPool(vrdxCudaDevice(0), 15, &pool_) != VK_SUCCESS) std::exit(2);
+    // VRDX_BENCH_NO_POOL=1: time with two CUDA events around the call (as the cuda backend is
+    // timed) instead of the 15-slot query pool, to expose the cost of the intermediate timestamps.
+    if (const char* e = std::getenv("VRDX_BENCH_NO_POOL")) no_pool_ = std::atoi(e) != 0;
+    CK(cudaEventCreate(&e0_));
+    CK(cudaEventCreate(&e1_));
   }
   ~B200Benchmark() override {
     cudaStreamSynchronize(stream_);
@@ -207,8 +212,10 @@ class B200Benchmark : public BenchmarkBase {
     CK(cudaMemcpyAsync(keys_.p, keys.data(), (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
     CK(cudaStreamSynchronize(stream_));
     const uint64_t c0 = NowNs();
+    if (no_pool_) CK(cudaEventRecord(e0_, stream_));
     vrdxCmdSort(vrdxCudaCommandBuffer(stream_), sorter_, n, vrdxCudaBuffer(keys_.p), 0, vrdxCudaBuffer(storage_.p), 0,
-                pool_, 0);
+                no_pool_ ? VK_NULL_HANDLE : pool_, 0);
+    if (no_pool_) CK(cudaEventRecord(e1_, stream_));
     CK(cudaStreamSynchronize(stream_));
     const uint64_t c1 = NowNs();
     Results r;
@@ -230,9 +237,11 @@ class B200Benchmark : public BenchmarkBase {
     CK(cudaMemcpyAsync(base + 2 * inout, &n, 4, cudaMemcpyHostToDevice, stream_));
     CK(cudaStreamSynchronize(stream_));
     const uint64_t c0 = NowNs();
+    if (no_pool_) CK(cudaEventRecord(e0_, stream_));
     vrdxCmdSortKeyValueIndirect(vrdxCudaCommandBuffer(stream_), sorter_, n, vrdxCudaBuffer(base), 2 * inout,
                                 vrdxCudaBuffer(base), 0, vrdxCudaBuffer(base), inout, vrdxCudaBuffer(storage_.p), 0,
-                                pool_, 0);
+                                no_pool_ ? VK_NULL_HANDLE : pool_, 0);
+    if (no_pool_) CK(cudaEventRecord(e1_, stream_));
     CK(cudaStreamSynchronize(stream_));
     const uint64_t c1 = NowNs();
     Results r;
@@ -250,10 +259,16 @@ class B200Benchmark : public BenchmarkBase {
       std::fprintf(stderr, "vrdx error: %s\n", vrdxCudaGetErrorString(e));
       std::exit(2);
     }
+    r.cpu_time = cpu_ns;
+    if (no_pool_) {
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, e0_, e1_));
+      r.total_time = (uint64_t)((double)ms * 1e6);
+      return;
+    }
     uint64_t ts[15] = {};
     vrdxCudaGetQueryPoolResults(pool_, 0, 15, ts);
     r.total_time = ts[14] - ts[0];
-    r.cpu_time = cpu_ns;
     for (int p = 0; p < 4; ++p) {  // same slot arithmetic as vulkan_benchmark.cc:330-337
       r.upsweep_ns += ts[2 + 3 * p] - ts[1 + 3 * p];
       r.spine_ns += ts[3 + 3 * p] - ts[2 + 3 * p];
@@ -263,6 +278,8 @@ class B200Benchmark : public BenchmarkBase {
   cudaStream_t stream_{};
   VrdxSorter sorter_{};
   VkQueryPool pool_{};
+  bool no_pool_ = false;
+  cudaEvent_t e0_{}, e1_{};
   DeviceBuffer keys_, storage_;
 };
 

@@ -10,7 +10,8 @@
  *                                    CUDA graph restores record-once / replay-many)
  *   VkBuffer + VkDeviceSize      ->  device pointer base + byte offset (offsets multiple of 16,
  *                                    README.md:150 of the reference)
- *   VkQueryPool                  ->  vrdxCudaCreateQueryPool() object holding CUDA events
+ *   VkQueryPool                  ->  vrdxCudaCreateQueryPool() object: device memory the sort's kernels
+ *                                    stamp with the GPU global timer (like vkCmdWriteTimestamp)
  *   VkPipelineCache              ->  ignored
  *
  * Unlike the reference this is a compiled library, and the declarations are extern "C" so

@@ -3,7 +3,7 @@
  *
  * Nothing here exists in the reference; these are the pieces a CUDA caller needs because
  * the Vulkan objects the reference API mentions are opaque handles on this backend:
- * handle constructors, a query-pool object made of CUDA events, an error channel (the
+ * handle constructors, a query-pool object of GPU-written timestamps, an error channel (the
  * reference's vrdxCmd* return void, src/vk_radix_sort.h.in:51-81), creation options for
  * A/B measurement, and an import path for a Vulkan application's exported VkDeviceMemory.
  * Plain C ABI: pointers and integers only.
@@ -74,7 +74,9 @@ uint32_t vrdxCudaGetLastLaunchCount(VrdxSorter sorter);
 
 /* ------------------------------------------------------------------ timestamps */
 
-/* A VkQueryPool made of `queryCount` CUDA events on `device` (>= 15 for one sort). */
+/* A VkQueryPool of `queryCount` timestamp slots on `device` (>= 15 for one sort).  The slots are
+ * device memory written by the sort's own kernels with the GPU global timer (nanoseconds), as
+ * vkCmdWriteTimestamp would: no extra stream operations, legal inside CUDA-graph capture. */
 VkResult vrdxCudaCreateQueryPool(VkDevice device, uint32_t queryCount, VkQueryPool* pQueryPool);
 void vrdxCudaDestroyQueryPool(VkQueryPool queryPool);
 /* After the stream has been synchronised: nanosecond timestamps of slots

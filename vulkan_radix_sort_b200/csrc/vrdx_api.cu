@@ -102,7 +102,7 @@ template <class Cfg>
 cudaError_t LaunchUpsweep(cudaStream_t stream, uint32_t grid, const PassArgs& args) {
   // the first kernel of a sort (pass 0) is a normal launch: it must wait for the caller's prior work
   return LaunchEx(UpsweepKernel<Cfg::kTile>, grid, kUpsweepThreads, 0, stream, args.pass != 0, args.indirect,
-                  args.n_or_max, args.pass, args.keys_in, args.status, args.status_next, args.hdr);
+                  args.n_or_max, args.pass, args.keys_in, args.status, args.status_next, args.hdr, args.ts_end);
 }
 template <int T, int I, bool KV, int M, int LB = 4>
 constexpr PassVariant MakeVariant() {
@@ -210,10 +210,15 @@ struct VrdxSorter_T {
   std::atomic<uint32_t> last_launches{0};
 };
 
+// A VkQueryPool on this backend: device memory the sort's own kernels stamp with %globaltimer
+// (like vkCmdWriteTimestamp, the write happens on the GPU timeline and costs no stream
+// serialisation).  Slots that coincide (no kernel between them) alias an earlier slot.
 struct VrdxQueryPool_T {
   int device = 0;
-  std::vector<cudaEvent_t> events;
-  std::vector<uint8_t> recorded;
+  uint32_t count = 0;
+  unsigned long long* d_slots = nullptr;
+  std::vector<int32_t> alias;     // slot -> slot whose device value it reports (itself if written by a kernel)
+  std::vector<uint8_t> recorded;  // a sort has been enqueued that writes this slot
 };
 
 struct VrdxCudaImportedMemory_T {
@@ -247,21 +252,27 @@ void NoteError(VrdxSorter s, cudaError_t e) {
 
 VrdxQueryPool_T* Pool(VkQueryPool p) { return reinterpret_cast<VrdxQueryPool_T*>(p); }
 
-void Stamp(VrdxSorter s, cudaStream_t stream, VkQueryPool pool, uint32_t slot) {
-  if (!pool) return;
-  VrdxQueryPool_T* qp = Pool(pool);
-  if (slot >= qp->events.size()) {
-    NoteError(s, cudaErrorInvalidValue);
-    return;
+// Query-pool bookkeeping of one sort: slot i of the sort lives at pool slot query + i.
+struct Stamps {
+  VrdxQueryPool_T* qp = nullptr;
+  uint32_t query = 0;
+  int last_written = 0;  // most recent slot a kernel writes
+  unsigned long long* Slot(int i) const { return qp ? qp->d_slots + query + i : nullptr; }
+  // slot i is written by the next kernel enqueued
+  unsigned long long* Written(int i) {
+    if (!qp) return nullptr;
+    qp->alias[query + i] = (int32_t)(query + i);
+    qp->recorded[query + i] = 1;
+    last_written = i;
+    return Slot(i);
   }
-  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  cudaStreamIsCapturing(stream, &cap);
-  cudaError_t e = (cap == cudaStreamCaptureStatusActive)
-                      ? cudaEventRecordWithFlags(qp->events[slot], stream, cudaEventRecordExternal)
-                      : cudaEventRecord(qp->events[slot], stream);
-  NoteError(s, e);
-  qp->recorded[slot] = 1;
-}
+  // slot i coincides with the latest written slot
+  void Same(int i) {
+    if (!qp) return;
+    qp->alias[query + i] = (int32_t)(query + last_written);
+    qp->recorded[query + i] = 1;
+  }
+};
 
 // The body of every vrdxCmdSort* (reference: gpuSort, h.in:344-507).
 void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or_max,
@@ -283,10 +294,21 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
   char* storage = addr(storageBuffer, storageOffset);
   const bool kv = values != nullptr;
 
-  Stamp(sorter, stream, queryPool, query + 0);
+  Stamps st;
+  if (queryPool) {
+    VrdxQueryPool_T* qp = Pool(queryPool);
+    if ((uint64_t)query + 15 > qp->count) {
+      NoteError(sorter, cudaErrorInvalidValue);
+    } else {
+      st.qp = qp;
+      st.query = query;
+      StampStartKernel<<<1, 32, 0, stream>>>(st.Written(0), 15);
+      NoteError(sorter, cudaGetLastError());
+    }
+  }
   if (n_or_max == 0 || !keys || !storage) {
     if (n_or_max != 0) NoteError(sorter, cudaErrorInvalidValue);
-    for (uint32_t i = 1; i < 15; ++i) Stamp(sorter, stream, queryPool, query + i);
+    for (int i = 1; i < 15; ++i) st.Same(i);
     sorter->last_launches.store(0);
     return;
   }
@@ -330,10 +352,11 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
     uint64_t cap = (uint64_t)sorter->sm_count * 4;
     uint32_t grid = (uint32_t)(chunks < cap ? (chunks ? chunks : 1) : cap);
     NoteError(sorter, LaunchEx(HistogramKernel, grid, kHistThreads, 0, stream, false, (const uint32_t*)keys, indirect,
-                               n_or_max, hdr));
+                               n_or_max, hdr, st.Written(1)));
     ++launches;
-  }  // reduce-then-scan keeps no state across passes: every table it reads is written first
-  Stamp(sorter, stream, queryPool, query + 1);
+  } else {
+    st.Same(1);  // reduce-then-scan keeps no state across passes: every table it reads is written first
+  }
 
   for (uint32_t pass = 0; pass < (uint32_t)kPasses; ++pass) {
     PassArgs args{};
@@ -355,31 +378,31 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
       args.status = status[0];
       args.status_next = status[1];
       const uint32_t chunks = (uint32_t)CeilDiv(tiles, (uint64_t)kSpineChunk);
+      args.ts_end = st.Written(2 + 3 * pass + 0);
       NoteError(sorter, variant.launch_upsweep(stream, chunks, args));
-      Stamp(sorter, stream, queryPool, query + 2 + 3 * pass + 0);
       // spine scratch: chunk prefixes occupy rows [0, chunks) of status B, segment sums the rows after them
       uint32_t* seg = status[1] + (size_t)chunks * kRadix;
       const uint32_t seg_grid = chunks < (uint32_t)kSpineSegments ? (chunks ? chunks : 1u) : (uint32_t)kSpineSegments;
       NoteError(sorter, LaunchEx(SpineReduceKernel, seg_grid, (uint32_t)kRadix, 0, stream, true, indirect,
                                  n_or_max, variant.tile, pass, (const uint32_t*)status[1], seg, hdr));
       NoteError(sorter, LaunchEx(SpineApplyKernel, seg_grid, (uint32_t)kRadix, 0, stream, true, indirect,
-                                 n_or_max, variant.tile, status[1], (const uint32_t*)seg));
-      Stamp(sorter, stream, queryPool, query + 2 + 3 * pass + 1);
+                                 n_or_max, variant.tile, status[1], (const uint32_t*)seg,
+                                 st.Written(2 + 3 * pass + 1)));
+      args.ts_end = st.Written(2 + 3 * pass + 2);
       NoteError(sorter, variant.launch_downsweep(stream, use_tma ? pass_grid : tiles, args));
       launches += 4;
-      Stamp(sorter, stream, queryPool, query + 2 + 3 * pass + 2);
       continue;
     }
     // One fused kernel per pass: the reference's upsweep and spine slots collapse onto its start.
-    Stamp(sorter, stream, queryPool, query + 2 + 3 * pass + 0);
-    Stamp(sorter, stream, queryPool, query + 2 + 3 * pass + 1);
+    st.Same(2 + 3 * pass + 0);
+    st.Same(2 + 3 * pass + 1);
+    args.ts_end = st.Written(2 + 3 * pass + 2);
     static const bool inorder = getenv("VRDX_TILE_ORDER") && atoi(getenv("VRDX_TILE_ORDER")) == 1;
     NoteError(sorter, (inorder && variant.launch_inorder) ? variant.launch_inorder(stream, pass_grid, args)
                                                           : variant.launch(stream, pass_grid, args));
     ++launches;
-    Stamp(sorter, stream, queryPool, query + 2 + 3 * pass + 2);
   }
-  Stamp(sorter, stream, queryPool, query + 14);
+  st.Same(14);
   sorter->last_launches.store(launches);
 }
 
@@ -567,15 +590,15 @@ VkResult vrdxCudaCreateQueryPool(VkDevice device, uint32_t queryCount, VkQueryPo
   VrdxQueryPool_T* qp = new (std::nothrow) VrdxQueryPool_T();
   if (!qp) return VK_ERROR_OUT_OF_HOST_MEMORY;
   qp->device = dev;
-  qp->events.resize(queryCount, nullptr);
+  qp->count = queryCount;
+  qp->alias.assign(queryCount, -1);
   qp->recorded.assign(queryCount, 0);
-  for (uint32_t i = 0; i < queryCount; ++i) {
-    if (cudaEventCreate(&qp->events[i]) != cudaSuccess) {
-      for (uint32_t j = 0; j < i; ++j) cudaEventDestroy(qp->events[j]);
-      delete qp;
-      cudaGetLastError();
-      return VK_ERROR_OUT_OF_DEVICE_MEMORY;
-    }
+  if (cudaMalloc(&qp->d_slots, sizeof(unsigned long long) * queryCount) != cudaSuccess ||
+      cudaMemset(qp->d_slots, 0, sizeof(unsigned long long) * queryCount) != cudaSuccess) {
+    cudaGetLastError();
+    if (qp->d_slots) cudaFree(qp->d_slots);
+    delete qp;
+    return VK_ERROR_OUT_OF_DEVICE_MEMORY;
   }
   *pQueryPool = reinterpret_cast<VkQueryPool>(qp);
   return VK_SUCCESS;
@@ -585,7 +608,7 @@ void vrdxCudaDestroyQueryPool(VkQueryPool queryPool) {
   if (!queryPool) return;
   VrdxQueryPool_T* qp = Pool(queryPool);
   DeviceGuard guard(qp->device);
-  for (cudaEvent_t e : qp->events) cudaEventDestroy(e);
+  cudaFree(qp->d_slots);
   delete qp;
 }
 
@@ -593,25 +616,24 @@ VkResult vrdxCudaGetQueryPoolResults(VkQueryPool queryPool, uint32_t firstQuery,
                                      uint32_t queryCount, uint64_t* pNanoseconds) {
   if (!queryPool || !pNanoseconds) return VK_ERROR_INITIALIZATION_FAILED;
   VrdxQueryPool_T* qp = Pool(queryPool);
-  if ((uint64_t)firstQuery + queryCount > qp->events.size()) return VK_ERROR_INITIALIZATION_FAILED;
-  DeviceGuard guard(qp->device);
-  double t = 0.0;  // accumulate slot-to-slot so float milliseconds never lose resolution
-  for (uint32_t i = 0; i < queryCount; ++i) {
+  if ((uint64_t)firstQuery + queryCount > qp->count) return VK_ERROR_INITIALIZATION_FAILED;
+  for (uint32_t i = 0; i < queryCount; ++i)
     if (!qp->recorded[firstQuery + i]) return VK_NOT_READY;
-    if (i > 0) {
-      float ms = 0.f;
-      cudaError_t e = cudaEventElapsedTime(&ms, qp->events[firstQuery + i - 1], qp->events[firstQuery + i]);
-      if (e == cudaErrorNotReady) {
-        cudaGetLastError();
-        return VK_NOT_READY;
-      }
-      if (e != cudaSuccess) {
-        cudaGetLastError();
-        return VK_ERROR_UNKNOWN;
-      }
-      t += (double)ms * 1e6;
-    }
-    pNanoseconds[i] = (uint64_t)(t + 0.5);
+  DeviceGuard guard(qp->device);
+  std::vector<unsigned long long> host(qp->count);
+  if (cudaMemcpy(host.data(), qp->d_slots, sizeof(unsigned long long) * qp->count, cudaMemcpyDeviceToHost) !=
+      cudaSuccess) {
+    cudaGetLastError();
+    return VK_ERROR_UNKNOWN;
+  }
+  unsigned long long prev = 0, base = 0;
+  for (uint32_t i = 0; i < queryCount; ++i) {
+    unsigned long long t = host[qp->alias[firstQuery + i]];
+    if (t == 0) return VK_NOT_READY;  // the kernel that writes this slot has not finished
+    if (t < prev) t = prev;           // stages of one sort are ordered; guard against timer granularity
+    if (i == 0) base = t;
+    pNanoseconds[i] = t - base;
+    prev = t;
   }
   return VK_SUCCESS;
 }

@@ -42,6 +42,23 @@ __device__ __forceinline__ uint32_t LdStream(const uint32_t* p) { return __ldcs(
 // Both are no-ops when the kernel was launched without the programmatic-serialization attribute.
 __device__ __forceinline__ void GridDepLaunch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void GridDepWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Device-written timestamps (the CUDA stand-in for vkCmdWriteTimestamp): nanoseconds of the
+// global timer; a kernel's "end of stage" stamp is the maximum over its CTAs.
+__device__ __forceinline__ unsigned long long GlobalTimerNs() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void StampEnd(unsigned long long* slot) {
+  if (slot != nullptr && threadIdx.x == 0) atomicMax(slot, GlobalTimerNs());
+}
+// First operation of a sort when a query pool is attached: clears the 15 slots and writes slot 0.
+__global__ void StampStartKernel(unsigned long long* slots, int count) {
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < count; ++i) slots[i] = 0ull;
+    slots[0] = GlobalTimerNs();
+  }
+}
 __device__ __forceinline__ uint32_t LaneMaskLt() {
   uint32_t m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -83,7 +100,7 @@ __device__ __forceinline__ void HistCount(uint32_t (*sh)[kRadix], uint32_t k) {
 
 __global__ void __launch_bounds__(kHistThreads)
 HistogramKernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ indirect,
-                uint32_t n_or_max, StorageHeader* __restrict__ hdr) {
+                uint32_t n_or_max, StorageHeader* __restrict__ hdr, unsigned long long* ts_end) {
   __shared__ uint32_t sh[kPasses][kRadix];
   __shared__ uint32_t s_last;
   const int tid = threadIdx.x;
@@ -142,6 +159,7 @@ HistogramKernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ 
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  StampEnd(ts_end);  // the last CTA ends the stage (its scan below is a few hundred cycles)
 
   // Last CTA: exclusive scan of each 256-bin histogram in place (spine.slang:62-83 does this
   // once per pass in workgroup 0; here once per sort).  Warp p scans pass p, 8 bins per lane.
@@ -194,6 +212,7 @@ struct PassArgs {
   uint32_t* keys_out;
   const uint32_t* vals_in;
   uint32_t* vals_out;
+  unsigned long long* ts_end;  // query-pool slot stamped when this kernel finishes (or nullptr)
 };
 
 constexpr int kSpineChunk = 8;         // reduce-then-scan: tiles per upsweep CTA / spine chunk
@@ -369,6 +388,7 @@ OnesweepKernel(const PassArgs a) {
         if (KV) a.vals_out[tile_start + idx] = cv[i];
       }
     }
+    StampEnd(a.ts_end);
     return;
   }
 
@@ -503,6 +523,7 @@ OnesweepKernel(const PassArgs a) {
       if (KV) a.vals_out[g] = s_vals[slot];
     }
   }
+  StampEnd(a.ts_end);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -692,6 +713,7 @@ OnesweepClusterKernel(const PassArgs a) {
       }
     }
   }
+  StampEnd(a.ts_end);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -715,7 +737,7 @@ template <int TILE>
 __global__ void __launch_bounds__(kUpsweepThreads)
 UpsweepKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t pass,
               const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ tile_hist,
-              uint32_t* __restrict__ chunk_sums, StorageHeader* __restrict__ hdr) {
+              uint32_t* __restrict__ chunk_sums, StorageHeader* __restrict__ hdr, unsigned long long* ts_end) {
   constexpr int THREADS = kUpsweepThreads;
   static_assert(THREADS == kRadix, "one thread per digit");
   __shared__ uint32_t h[2][kRadix];
@@ -760,6 +782,7 @@ UpsweepKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t
     chunk_acc += c;
   }
   chunk_sums[(size_t)blockIdx.x * kRadix + tid] = chunk_acc;
+  StampEnd(ts_end);
 }
 
 // Spine: exclusive scan of chunk_sums[chunk][256] over chunks for every digit, and the global
@@ -829,7 +852,7 @@ SpineReduceKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint
 
 __global__ void __launch_bounds__(kRadix)
 SpineApplyKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t tile_size,
-                 uint32_t* __restrict__ chunk_sums, const uint32_t* __restrict__ seg) {
+                 uint32_t* __restrict__ chunk_sums, const uint32_t* __restrict__ seg, unsigned long long* ts_end) {
   GridDepLaunch();
   GridDepWait();
   const uint32_t n = ResolveCount(indirect, n_or_max);
@@ -849,6 +872,7 @@ SpineApplyKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint3
       run += v[j];
     }
   }
+  StampEnd(ts_end);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1124,6 +1148,7 @@ OnesweepTmaKernel(const PassArgs a) {
     }
     // s_misc[8+slot] is next read two iterations from now, after several barriers
   }
+  StampEnd(a.ts_end);
 }
 
 }  // namespace vrdx
