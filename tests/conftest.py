@@ -38,7 +38,8 @@ FLAVOURS = {
     "reduce_then_scan": ("REDUCE_THEN_SCAN", "DIRECT", None),
     "onesweep_tma_persistent": ("ONESWEEP", "TMA", None),
     "reduce_then_scan_tma_persistent": ("REDUCE_THEN_SCAN", "TMA", None),
-    "onesweep_cluster4_lookback": ("ONESWEEP", "DIRECT", (7, 7)),   # kKeysVariants[6] / kPairVariants[6]
+    "onesweep_cluster4_lookback": ("ONESWEEP", "DIRECT", (6, 6)),   # kKeysVariants[5] / kPairVariants[5]
+    "reduce_then_scan_paired_staging": ("REDUCE_THEN_SCAN", "DIRECT", (0, 0, 0, 0, 9)),  # k*Variants[8]
     "auto": ("AUTO", "AUTO", None),
 }
 

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vulkan_radix_sort_b200 import Sorter, api
 from vulkan_radix_sort_b200.datagen import make_keys
 flavours = {"onesweep": (1, 1, None), "rts": (2, 1, None), "onesweep_tma": (1, 2, None), "rts_tma": (2, 2, None),
-            "cluster4": (1, 1, (7, 7))}
+            "cluster4": (1, 1, (6, 6))}
 only = sys.argv[1:] or list(flavours)
 for name in only:
     algo, load, res = flavours[name]

@@ -104,9 +104,9 @@ cudaError_t LaunchUpsweep(cudaStream_t stream, uint32_t grid, const PassArgs& ar
   return LaunchEx(UpsweepKernel<Cfg::kTile>, grid, kUpsweepThreads, 0, stream, args.pass != 0, args.indirect,
                   args.n_or_max, args.pass, args.keys_in, args.status, args.status_next, args.hdr, args.ts_end);
 }
-template <int T, int I, bool KV, int M, int LB = 4>
+template <int T, int I, bool KV, int M, int LB = 4, bool PAIRED = false>
 constexpr PassVariant MakeVariant() {
-  using Cfg = PassConfig<T, I, KV, M, LB>;
+  using Cfg = PassConfig<T, I, KV, M, LB, PAIRED>;
   return PassVariant{T, I, M, false, 0, (uint32_t)Cfg::kTile, Cfg::kSmemBytes, &PrepareDirect<Cfg>,
                      &LaunchDirect<Cfg, 0>, &LaunchDirect<Cfg, 1>, &LaunchUpsweep<Cfg>, &LaunchDirect<Cfg, 2>};
 }
@@ -155,26 +155,21 @@ constexpr PassVariant MakeTmaVariant() {
 //   onesweep, keys and pairs      index 0  384 x 16, 3 CTAs/SM
 //   reduce-then-scan, keys        index 1  256 x 16, 5 CTAs/SM   (no look-back state in registers)
 //   reduce-then-scan, pairs       index 0
-// The rest are kept selectable for A/B runs (VrdxCudaSorterOptions::reserved / VRDX_*_VARIANT).
+// The rest are kept selectable for A/B runs (VrdxCudaSorterOptions::reserved / VRDX_*_VARIANT) and
+// are exercised by the test-suite where they change the algorithm (cluster look-back, paired staging).
 static const PassVariant kKeysVariants[] = {
     MakeVariant<384, 16, false, 3>(),           MakeVariant<256, 16, false, 5>(),
     MakeVariant<512, 16, false, 2>(),           MakeVariant<256, 16, false, 4>(),
-    MakeVariant<384, 12, false, 4>(),           MakeVariant<256, 12, false, 6>(),
-    MakeClusterVariant<384, 16, false, 3, 4>(), MakeClusterVariant<384, 16, false, 3, 8>(),
-    MakeVariant<256, 16, false, 6>(),           MakeVariant<256, 20, false, 4>(),
-    MakeVariant<320, 16, false, 4>(),           MakeVariant<256, 24, false, 3>(),
-    MakeVariant<384, 16, false, 3, 16>(),       MakeVariant<256, 16, false, 4, 16>(),
-    MakeVariant<256, 8, false, 6, 16>(),        MakeVariant<256, 8, false, 6, 32>(),
+    MakeVariant<384, 12, false, 4>(),           MakeClusterVariant<384, 16, false, 3, 4>(),
+    MakeClusterVariant<384, 16, false, 3, 8>(), MakeVariant<384, 16, false, 3, 16>(),
+    MakeVariant<384, 16, false, 3>(),  // placeholder so keys and pairs tables index alike
 };
 static const PassVariant kPairVariants[] = {
     MakeVariant<384, 16, true, 3>(),            MakeVariant<256, 16, true, 5>(),
     MakeVariant<512, 16, true, 2>(),            MakeVariant<256, 16, true, 4>(),
-    MakeVariant<384, 12, true, 4>(),            MakeVariant<256, 12, true, 6>(),
-    MakeClusterVariant<384, 16, true, 3, 4>(),  MakeClusterVariant<384, 16, true, 3, 8>(),
-    MakeVariant<256, 16, true, 6>(),            MakeVariant<256, 20, true, 4>(),
-    MakeVariant<320, 16, true, 4>(),            MakeVariant<256, 24, true, 3>(),
-    MakeVariant<384, 16, true, 3, 16>(),        MakeVariant<256, 16, true, 4, 16>(),
-    MakeVariant<256, 8, true, 6, 16>(),         MakeVariant<256, 8, true, 6, 32>(),
+    MakeVariant<384, 12, true, 4>(),            MakeClusterVariant<384, 16, true, 3, 4>(),
+    MakeClusterVariant<384, 16, true, 3, 8>(),  MakeVariant<384, 16, true, 3, 16>(),
+    MakeVariant<384, 16, true, 3, 4, true>(),  // (key, value) staged as one 64-bit element: measured slower
 };
 constexpr int kDefaultKeysRtsVariant = 1;
 constexpr int kDefaultPairRtsVariant = 0;
@@ -191,7 +186,7 @@ constexpr int kNumPairVariants = sizeof(kPairVariants) / sizeof(kPairVariants[0]
 constexpr int kNumKeysTmaVariants = sizeof(kKeysTmaVariants) / sizeof(kKeysTmaVariants[0]);
 constexpr int kNumPairTmaVariants = sizeof(kPairTmaVariants) / sizeof(kPairTmaVariants[0]);
 // Smallest tile of any compiled variant: sizes the look-back buffers whichever variant runs.
-constexpr uint32_t kMinTile = 2048;  // 256 x 8
+constexpr uint32_t kMinTile = 4096;  // 256 x 16
 // AUTO: reduce-then-scan at and above this count, onesweep (fewer launches) below it.
 constexpr uint32_t kAutoRtsThreshold = 3u << 23;  // measured crossover between 2^24 and 2^25 (profiles/r01_sweep_n.txt)
 

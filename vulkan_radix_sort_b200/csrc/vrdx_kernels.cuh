@@ -218,9 +218,10 @@ struct PassArgs {
 constexpr int kSpineChunk = 8;         // reduce-then-scan: tiles per upsweep CTA / spine chunk
 constexpr int kRepairBallotThreshold = 12;  // colliding lanes above which the 8-round ballot loop is cheaper
 
-template <int THREADS, int IPT, bool KV, int MIN_CTAS, int LOOK_BATCH = 4>
+template <int THREADS, int IPT, bool KV, int MIN_CTAS, int LOOK_BATCH = 4, bool PAIRED = false>
 struct PassConfig {
   static constexpr int kLookBatch = LOOK_BATCH;  // look-back cells fetched per round trip
+  static constexpr bool kPaired = KV && PAIRED;  // key-value: stage (key, value) as one 64-bit shared-memory element
   static constexpr int kThreads = THREADS;
   static constexpr int kItems = IPT;
   static constexpr int kMinCtas = MIN_CTAS;
@@ -481,7 +482,7 @@ OnesweepKernel(const PassArgs a) {
     for (int i = 0; i < IPT; ++i) {
       const uint32_t d = (key[i] >> shift) & 0xFFu;
       rank[i] += base[d];
-      s_keys[rank[i]] = key[i];
+      if (!Cfg::kPaired) s_keys[rank[i]] = key[i];
     }
     if (KV) {
       // values are fetched only now, so they do not occupy registers during the ranking
@@ -489,8 +490,15 @@ OnesweepKernel(const PassArgs a) {
       uint32_t val[IPT];
 #pragma unroll
       for (int i = 0; i < IPT; ++i) val[i] = (full || woff + 32 * i < tile_count) ? LdStream(vin + 32 * i) : 0u;
+      if (Cfg::kPaired) {
+        // keys were not stored above (see kPaired there): one 64-bit store per pair
+        uint2* s_kv = reinterpret_cast<uint2*>(s_keys);
 #pragma unroll
-      for (int i = 0; i < IPT; ++i) s_vals[rank[i]] = val[i];
+        for (int i = 0; i < IPT; ++i) s_kv[rank[i]] = make_uint2(key[i], val[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) s_vals[rank[i]] = val[i];
+      }
     }
   }
 
@@ -516,11 +524,20 @@ OnesweepKernel(const PassArgs a) {
 #pragma unroll
   for (int i = 0; i < IPT; ++i) {
     const uint32_t slot = i * THREADS + tid;
-    const uint32_t k = s_keys[slot];
-    const uint32_t g = s_gbase[(k >> shift) & 0xFFu] + slot;
-    if (full || slot < tile_count) {
-      a.keys_out[g] = k;
-      if (KV) a.vals_out[g] = s_vals[slot];
+    if (Cfg::kPaired) {
+      const uint2 kv = reinterpret_cast<const uint2*>(s_keys)[slot];
+      const uint32_t g = s_gbase[(kv.x >> shift) & 0xFFu] + slot;
+      if (full || slot < tile_count) {
+        a.keys_out[g] = kv.x;
+        a.vals_out[g] = kv.y;
+      }
+    } else {
+      const uint32_t k = s_keys[slot];
+      const uint32_t g = s_gbase[(k >> shift) & 0xFFu] + slot;
+      if (full || slot < tile_count) {
+        a.keys_out[g] = k;
+        if (KV) a.vals_out[g] = s_vals[slot];
+      }
     }
   }
   StampEnd(a.ts_end);
