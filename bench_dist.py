@@ -51,7 +51,8 @@ def run(args, metric, unit):
     pristine = torch.from_numpy(host_keys.view(np.int32)).cuda()
     keys = torch.empty_like(pristine)
     backend = CudaBackend(local_rank)
-    cap = n + (n >> 6) + 1024                                    # exact splitters: every rank receives N/G +- 1
+    strategy = os.environ.get("VRDX_DIST_SPLITTERS", "sampled")      # sampled: ~1 % imbalance; exact: N/G +- 1
+    cap = n + (n >> 4) + 1024
     fused = os.environ.get("VRDX_DIST_EXCHANGE", "fused") != "nccl"
     shared = SharedReceive(backend, cap) if fused else None
     part = None if fused else torch.empty(n, dtype=torch.int32, device="cuda")
@@ -70,7 +71,7 @@ def run(args, metric, unit):
         torch.cuda.synchronize()
         tm = _Timers()
         _, recv_count, plan = distributed_sort(backend, keys, n, recv=recv, part=part, storage=storage, timers=tm,
-                                               shared=shared)
+                                               shared=shared, strategy=strategy)
         torch.cuda.synchronize()
         dist.barrier()
         if it >= warmup:
@@ -116,7 +117,8 @@ def run(args, metric, unit):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         keys.copy_(pinned_in, non_blocking=True)
-        _, rc, _ = distributed_sort(backend, keys, n, recv=recv, part=part, storage=storage, shared=shared)
+        _, rc, _ = distributed_sort(backend, keys, n, recv=recv, part=part, storage=storage, shared=shared,
+                                    strategy=strategy)
         pinned_out[:rc].copy_(recv[:rc], non_blocking=True)
         e1.record()
         torch.cuda.synchronize()
@@ -132,18 +134,18 @@ def run(args, metric, unit):
         peak, peak_src = measured_peak_gbs()
         stages = {k: statistics.mean(v) for k, v in stage_acc.items()}
         sort_ms = stages["local_sort"]
-        launches = backend.sorter.last_launch_count + 4 + 1      # local sort + 4 histogram levels + partition
+        launches = backend.sorter.last_launch_count + (3 if strategy == "exact" else 2) + 1  # local sort + splitter kernels + partition
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"distributed 32-bit keys-only sort, 2^{args.log2n_per_gpu} uniform keys per GPU "
-                                   f"(DataGenerator seed 1+rank), {world} GPUs: exact-splitter MSD partition "
+                                   f"(DataGenerator seed 1+rank), {world} GPUs: {strategy}-splitter MSD partition "
                                    + ("fused with the exchange (peer stores over NVLink)" if fused else "+ NCCL all-to-all-v")
                                    + " + local LSD sort",
                        "l2": "per-GPU inputs (2 GiB) larger than L2; restore copy between steps",
                        "timing": "CUDA events around the whole distributed sort on every rank, max over ranks",
-                       "verified": verified},
+                       "splitters": strategy, "verified": verified},
             "stages_ms_max_over_ranks": stages,
             # bytes leaving each GPU / time of the stage(s) that move them (fused: partition + barrier)
             "exchange_gbs_per_gpu": ((world - 1) / world * 4 * n /

@@ -46,6 +46,15 @@ void vrdxDistCmdPartition(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint
                           VkDeviceSize cursorsOffset, VkBuffer outBuffer, VkDeviceSize outOffset);
 
 /*
+ * Class sizes for the same splitters, without moving anything: counts[c] += #{ keys of class c }
+ * (2 * splitterCount + 1 uint32, zeroed by the caller).  One 4 B/key read.
+ */
+void vrdxDistCmdClassCount(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t elementCount,
+                           VkBuffer keysBuffer, VkDeviceSize keysOffset, uint32_t splitterCount,
+                           VkBuffer splittersBuffer, VkDeviceSize splittersOffset, VkBuffer countsBuffer,
+                           VkDeviceSize countsOffset);
+
+/*
  * Partition + exchange in ONE kernel.  Same multi-split as vrdxDistCmdPartition, but a key whose
  * class-ordered position is p, with firstPosition[j] <= p < firstPosition[j+1], is stored straight
  * into destination j's receive buffer at destPointers[j][p - firstPosition[j]] — peer memory

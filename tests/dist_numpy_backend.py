@@ -28,6 +28,13 @@ class NumpyBackend:
             out[j] = np.bincount(digit[sel], minlength=bins)
         return torch.from_numpy(out)
 
+    def class_count(self, keys, count, splitters):
+        k64 = _u32(keys, count).astype(np.uint64)
+        u = np.array(splitters.tolist(), dtype=np.uint64)
+        gt = (k64[:, None] > u[None, :]).sum(axis=1) if u.size else np.zeros(k64.size, dtype=np.int64)
+        eq = (k64[:, None] == u[None, :]).any(axis=1) if u.size else np.zeros(k64.size, dtype=bool)
+        return torch.from_numpy(np.bincount(2 * gt + eq, minlength=2 * u.size + 1).astype(np.int64))
+
     def partition(self, keys, count, splitters, class_starts, out):
         k = _u32(keys, count)
         u = np.array(splitters.tolist(), dtype=np.uint64)

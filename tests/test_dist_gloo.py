@@ -23,7 +23,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, dist_name, n_per_rank, q):
+def _worker(rank, world, port, dist_name, n_per_rank, q, strategy="exact"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -37,18 +37,18 @@ def _worker(rank, world, port, dist_name, n_per_rank, q):
         name = "uniform" if dist_name == "empty_rank" else dist_name
         keys_np = make_keys(name, max(n, 1), seed=1 + rank)[:n]
         keys = torch.from_numpy(keys_np.view(np.int32).copy())
-        recv, cnt, plan = distributed_sort(NumpyBackend(), keys, n)
+        recv, cnt, plan = distributed_sort(NumpyBackend(), keys, n, strategy=strategy)
         out = recv.numpy()[:cnt].view(np.uint32).copy()
         q.put((rank, keys_np, out, plan.total, plan.targets, plan.sizes))
     finally:
         dist.destroy_process_group()
 
 
-def _run(world, dist_name, n_per_rank):
+def _run(world, dist_name, n_per_rank, strategy="exact"):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, dist_name, n_per_rank, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, dist_name, n_per_rank, q, strategy)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=120) for _ in range(world)]
@@ -74,3 +74,16 @@ def test_distributed_sort_matches_oracle(oracle, world, dist_name):
         assert (t, tg) == (total, targets) and sizes == results[0][5]      # identical plan everywhere
         assert out.size == targets[rank + 1] - targets[rank]               # balanced to +-1 key, any distribution
         assert abs(out.size - total / world) <= 1
+
+
+@pytest.mark.parametrize("dist_name", ["uniform", "all_zero", "skewed", "empty_rank"])
+def test_sampled_splitters_sort_exactly_and_balance_approximately(oracle, dist_name):
+    world = 3
+    results = _run(world, dist_name, 20011, strategy="sampled")
+    union = np.concatenate([r[1] for r in results])
+    got = np.concatenate([r[2] for r in results])
+    assert np.array_equal(got, oracle.sort_keys(union))                  # exactly sorted whatever the splitters
+    total = results[0][3]
+    for rank, _, out, t, tg, sizes in results:
+        assert sizes == results[0][5]
+        assert abs(out.size - total / world) <= 0.03 * total / world + 2   # ~1 % sampling error; ties are cut exactly

@@ -46,6 +46,19 @@ def test_prefix_histogram_matches_numpy(backends, dist_name):
             assert torch.equal(got, want), (dist_name, n, shift, bits)
 
 
+@pytest.mark.parametrize("dist_name", ["uniform", "bits4", "all_ones", "sentinel_mix"])
+def test_class_count_matches_numpy(backends, dist_name):
+    from vulkan_radix_sort_b200.datagen import make_keys
+    cuda_b, np_b = backends
+    for n, splitters in ((1, []), (4097, [7]), (100003, [3, 0x40000000, 0xFFFFFFFF]),
+                         ((1 << 20) + 5, [0, 1, 2, 0x7FFFFFFF, 0x80000000, 0xC0000000, 0xFFFFFFFE])):
+        k = make_keys(dist_name, n, seed=6)
+        spl = torch.tensor(splitters, dtype=torch.int64)
+        want = np_b.class_count(torch.from_numpy(k.view(np.int32).copy()), n, spl)
+        got = cuda_b.class_count(_dev(k), n, spl.cuda()).cpu()
+        assert torch.equal(got, want), (dist_name, n)
+
+
 @pytest.mark.parametrize("dist_name", ["uniform", "bits4", "all_zero", "sentinel_mix"])
 def test_partition_groups_by_class(backends, dist_name):
     from vulkan_radix_sort_b200.datagen import make_keys
@@ -68,7 +81,7 @@ def test_partition_groups_by_class(backends, dist_name):
             assert np.array_equal(np.sort(got[a:a + sz]), np.sort(k[cls == c])), (dist_name, n, c)
 
 
-def _nccl_worker(rank, world, port, dist_name, n, q, fused=False):
+def _nccl_worker(rank, world, port, dist_name, n, q, fused=False, strategy="exact"):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -79,10 +92,10 @@ def _nccl_worker(rank, world, port, dist_name, n, q, fused=False):
         from vulkan_radix_sort_b200.dist import CudaBackend, SharedReceive, distributed_sort
         k = make_keys(dist_name, n + 13 * rank, seed=1 + rank)
         backend = CudaBackend(rank)
-        shared = SharedReceive(backend, n + 13 * world + 64) if fused else None
+        shared = SharedReceive(backend, int(n * 1.1) + 1024) if fused else None
         for _ in range(2):  # twice: the receive buffers are reused across sorts
             recv, cnt, plan = distributed_sort(backend, torch.from_numpy(k.view(np.int32).copy()).cuda(), k.size,
-                                               shared=shared)
+                                               shared=shared, strategy=strategy)
             torch.cuda.synchronize()
         q.put((rank, k, recv[:cnt].cpu().numpy().view(np.uint32).copy(), plan.targets))
         if shared is not None:
@@ -92,9 +105,12 @@ def _nccl_worker(rank, world, port, dist_name, n, q, fused=False):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("strategy", ["exact", "sampled"])
 @pytest.mark.parametrize("fused", [False, True], ids=["nccl_all_to_all", "fused_peer_stores"])
 @pytest.mark.parametrize("dist_name", ["uniform", "all_zero", "skewed"])
-def test_distributed_sort_over_nccl(oracle, dist_name, fused):
+def test_distributed_sort_over_nccl(oracle, dist_name, fused, strategy):
+    if strategy == "sampled" and not fused:
+        pytest.skip("sampled splitters are covered with the fused exchange")
     world = torch.cuda.device_count()
     if world < 2:
         pytest.skip("needs at least two GPUs")
@@ -104,7 +120,7 @@ def test_distributed_sort_over_nccl(oracle, dist_name, fused):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, dist_name, 3_000_017, q, fused)) for r in range(world)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, dist_name, 3_000_017, q, fused, strategy)) for r in range(world)]
     for p in procs:
         p.start()
     results = sorted([q.get(timeout=300) for _ in range(world)], key=lambda r: r[0])
@@ -114,4 +130,8 @@ def test_distributed_sort_over_nccl(oracle, dist_name, fused):
     union = np.concatenate([r[1] for r in results])
     assert np.array_equal(np.concatenate([r[2] for r in results]), oracle.sort_keys(union))
     for rank, _, out, targets in results:
-        assert out.size == targets[rank + 1] - targets[rank]
+        want = targets[rank + 1] - targets[rank]
+        if strategy == "exact":
+            assert out.size == want
+        else:
+            assert abs(out.size - want) <= 0.03 * want + 2

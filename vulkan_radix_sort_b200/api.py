@@ -85,6 +85,8 @@ _SIGNATURES = {
     # include/vrdx_dist.h
     "vrdxDistCmdPrefixHistogram": (None, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_uint32, c_uint32, c_uint32,
                                           c_void_p, c_uint64, c_void_p, c_uint64]),
+    "vrdxDistCmdClassCount": (None, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_uint32, c_void_p, c_uint64,
+                                     c_void_p, c_uint64]),
     "vrdxDistCmdPartitionScatter": (None, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_uint32, c_void_p, c_uint64,
                                            c_void_p, c_uint64, c_uint32, c_void_p, c_uint64]),
     "vrdxDistAllocShared": (c_int, [c_void_p, c_uint64, POINTER(c_void_p), ctypes.c_char_p]),

@@ -736,6 +736,31 @@ void vrdxDistCmdPrefixHistogram(VkCommandBuffer commandBuffer, VrdxSorter sorter
   NoteError(sorter, cudaGetLastError());
 }
 
+void vrdxDistCmdClassCount(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t elementCount,
+                           VkBuffer keysBuffer, VkDeviceSize keysOffset, uint32_t splitterCount,
+                           VkBuffer splittersBuffer, VkDeviceSize splittersOffset, VkBuffer countsBuffer,
+                           VkDeviceSize countsOffset) {
+  if (!sorter) return;
+  if (!keysBuffer || !countsBuffer || splitterCount > (uint32_t)kDistMaxSplitters ||
+      (splitterCount && !splittersBuffer)) {
+    NoteError(sorter, cudaErrorInvalidValue);
+    return;
+  }
+  if (elementCount == 0) return;
+  DeviceGuard guard(sorter->device);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(commandBuffer);
+  const uint32_t* keys = reinterpret_cast<const uint32_t*>(reinterpret_cast<char*>(keysBuffer) + keysOffset);
+  const uint32_t* splitters =
+      splittersBuffer ? reinterpret_cast<const uint32_t*>(reinterpret_cast<char*>(splittersBuffer) + splittersOffset)
+                      : keys;
+  uint32_t* counts = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(countsBuffer) + countsOffset);
+  const uint64_t blocks = CeilDiv((uint64_t)elementCount, (uint64_t)kDistHistThreads);
+  const uint64_t cap = (uint64_t)sorter->sm_count * 4;
+  DistClassCountKernel<<<(uint32_t)(blocks < cap ? blocks : cap), kDistHistThreads, 0, stream>>>(
+      keys, elementCount, splitterCount, splitters, counts);
+  NoteError(sorter, cudaGetLastError());
+}
+
 namespace {
 void EnqueuePartition(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t elementCount, VkBuffer keysBuffer,
                       VkDeviceSize keysOffset, uint32_t splitterCount, VkBuffer splittersBuffer,

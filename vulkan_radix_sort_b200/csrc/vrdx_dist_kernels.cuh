@@ -98,6 +98,68 @@ DistPrefixHistogramKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_
   }
 }
 
+// ---- class sizes (count only) ----------------------------------------------------------------------
+// Same class function as the multi-split below; warp-aggregated shared-memory counting (a class is
+// shared by many lanes, so peers are found with a ballot per class bit instead of colliding atomics).
+__global__ void __launch_bounds__(kDistHistThreads)
+DistClassCountKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t splitter_count,
+                     const uint32_t* __restrict__ splitters, uint32_t* __restrict__ counts) {
+  __shared__ uint32_t s_u[kDistMaxSplitters];
+  __shared__ uint32_t s_top[kRadix];
+  __shared__ uint32_t s_cnt[32];
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid < (int)splitter_count) s_u[tid] = splitters[tid];
+  if (tid < 32) s_cnt[tid] = 0;
+  if (tid < kRadix) {
+    uint32_t below = 0, inside = 0;
+    for (uint32_t j = 0; j < splitter_count; ++j) {
+      const uint32_t ub = splitters[j] >> 24;
+      below += ub < (uint32_t)tid;
+      inside |= ub == (uint32_t)tid;
+    }
+    s_top[tid] = inside ? 0x80000000u : 2u * below;
+  }
+  __syncthreads();
+  auto class_of = [&](uint32_t k) -> uint32_t {
+    const uint32_t t = s_top[k >> 24];
+    if (!(t & 0x80000000u)) return t;
+    uint32_t gt = 0, eq = 0;
+    for (uint32_t j = 0; j < splitter_count; ++j) {
+      gt += k > s_u[j];
+      eq |= k == s_u[j];
+    }
+    return 2u * gt + eq;
+  };
+  auto count_class = [&](uint32_t c, bool valid) {
+    // lanes of the warp holding class c: one atomic per (warp, class) group
+    uint32_t peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+      const bool bit = (c >> b) & 1u;
+      const uint32_t m = __ballot_sync(0xffffffffu, bit);
+      peers &= bit ? m : ~m;
+    }
+    if (valid && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s_cnt[c], __popc(peers));
+  };
+  const uint64_t stride = (uint64_t)gridDim.x * kDistHistThreads;
+  const uint64_t rounds = ((uint64_t)n + stride - 1) / stride;
+  constexpr int kUnroll = 8;  // loads in flight per thread
+  for (uint64_t r0 = 0; r0 < rounds; r0 += kUnroll) {  // warp-uniform trip count (ballots inside)
+    uint32_t k[kUnroll];
+    bool valid[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint64_t i = (r0 + u) * stride + (uint64_t)blockIdx.x * kDistHistThreads + tid;
+      valid[u] = (r0 + u) < rounds && i < n;
+      k[u] = valid[u] ? LdStream(keys + i) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) count_class(valid[u] ? class_of(k[u]) : 0u, valid[u]);
+  }
+  __syncthreads();
+  if (tid < (int)(2 * splitter_count + 1) && s_cnt[tid]) atomicAdd(&counts[tid], s_cnt[tid]);
+}
+
 // ---- class multi-split ------------------------------------------------------------------------
 // One tile per CTA; a class is a 5-bit label, so peers inside a warp come from a 5-round ballot
 // loop (cheap here: 5 instead of 8 rounds, and the kernel runs once per sort).  Tile-local reorder

@@ -2,12 +2,13 @@
 
 BASELINE.json configs[4] / SURVEY.md §8(e).  The reference is single-device; this layer is new:
 
-  1. exact splitters — a 4-level (8 bits per level) distributed histogram search finds, for every
-     boundary k = 1..G-1, the key value v_k at global rank T_k = k*N/G together with the number of
-     keys below it and equal to it (globally and per rank).  Cost: four 4 B/key reads of the local
-     keys and four tiny all-reduces.  The partition is balanced to +-1 key for ANY input
-     distribution: ties on a splitter value (an all-equal input is one big tie) are split by
-     source rank, which is legal for a keys-only sort because equal keys are indistinguishable;
+  1. splitters.  Default ("sampled"): every rank contributes 2^16 evenly strided keys, the sorted
+     sample gives the G-1 splitter values, and ONE exact class-count pass over the local keys
+     (vrdxDistCmdClassCount, 4 B/key) gives every (rank, class) size.  Alternative ("exact"): a
+     3-level (8/12/12-bit) distributed histogram search finds the key value at every global rank
+     k*N/G (three 4 B/key passes); every rank then receives N/G +- 1 keys.  In both, ties on a
+     splitter value (an all-equal input is one big tie) are cut exactly and handed out by source
+     rank, which is legal for a keys-only sort because equal keys are indistinguishable;
   2. local multi-split (vrdxDistCmdPartition) into <= 2G-1 classes (open intervals between
      splitters and one tie class per distinct splitter value), class-ordered, so the keys bound
      for each destination rank are ONE contiguous slice of the output;
@@ -68,6 +69,17 @@ class CudaBackend:
             hist.data_ptr(), 0)
         self.sorter.check()
         return (hist.to(torch.int64) & 0xFFFFFFFF).view(p, 1 << bits)
+
+    def class_count(self, keys: torch.Tensor, count: int, splitters: torch.Tensor) -> torch.Tensor:
+        """-> int64 [2m+1]: local number of keys in every class of the given distinct splitters."""
+        m = int(splitters.numel())
+        spl = _u32_as_i32(splitters) if m else None
+        counts = torch.zeros(2 * m + 1, dtype=torch.int32, device=self.device)
+        self.api.load_library().vrdxDistCmdClassCount(
+            self._stream(), self.sorter.handle, count, keys.data_ptr(), 0, m, spl.data_ptr() if m else None, 0,
+            counts.data_ptr(), 0)
+        self.sorter.check()
+        return counts.to(torch.int64) & 0xFFFFFFFF
 
     def partition_scatter(self, keys: torch.Tensor, count: int, splitters: torch.Tensor, class_starts: torch.Tensor,
                           dest_ptrs, first_pos) -> None:
@@ -222,47 +234,114 @@ def find_splitters(backend, keys: torch.Tensor, count: int, group=None):
     return as_list(prefix), as_list(less_g), as_list(eq_g), as_list(less_l), as_list(eq_l), total, targets
 
 
-def make_plan(backend, keys: torch.Tensor, count: int, group=None) -> SplitPlan:
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    v, less_g, eq_g, less_l, eq_l, total, targets = find_splitters(backend, keys, count, group)
+SAMPLES_PER_RANK = 1 << 16
+
+
+def _plan_from_class_stats(world, rank, total, targets, values, less_g, eq_g, counts, less_l_all, eq_l_all):
+    """Common tail of both strategies.  `values[k]` is the splitter of boundary k+1; less/eq are the
+    numbers of keys below / equal to it (globally, and per rank).  Boundary k+1 is placed at global
+    rank clamp(T_{k+1}, less_g, less_g + eq_g): inside a tie class the cut is exact, and ties are
+    handed out to the left side by source rank order."""
     nb = world - 1
-    # every rank's local statistics: [count, less_l(1..nb), eq_l(1..nb)]
-    mine = torch.tensor([count] + less_l + eq_l, dtype=torch.int64, device=keys.device)
-    everyone = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(everyone, mine, group=group)
-    stats = torch.stack(everyone).cpu().tolist()
-    v_h, less_g_h = v, less_g
-    counts = [int(r[0]) for r in stats]
-    less_l_all = [[int(x) for x in r[1:1 + nb]] for r in stats]
-    eq_l_all = [[int(x) for x in r[1 + nb:1 + 2 * nb]] for r in stats]
-    # local boundary positions a[s][k]: the first a[s][k] keys (in class order) of rank s go to ranks < k
     sizes = []
     for s in range(world):
         a = [0]
         for k in range(nb):
-            need_left = targets[k + 1] - less_g_h[k]             # ties that must end up left of boundary k+1, globally
-            before = sum(eq_l_all[t][k] for t in range(s))       # ties held by lower ranks go first
+            need_left = min(max(targets[k + 1] - less_g[k], 0), eq_g[k])   # ties that end up left of boundary k+1
+            before = sum(eq_l_all[t][k] for t in range(s))                  # ties held by lower ranks go first
             left = min(max(need_left - before, 0), eq_l_all[s][k])
             a.append(less_l_all[s][k] + left)
         a.append(counts[s])
-        for k in range(1, len(a)):                               # duplicates among splitters keep positions monotone
+        for k in range(1, len(a)):                                          # repeated splitter values keep positions monotone
             a[k] = max(a[k], a[k - 1])
         sizes.append([a[j + 1] - a[j] for j in range(world)])
-    distinct = sorted(set(int(x) for x in v_h))
-    # class layout of THIS rank: [interior_0][tie_0][interior_1][tie_1]...[interior_m]
+    distinct = sorted(set(values))
     starts = [0]
-    for u in distinct:
-        k = v_h.index(u)
-        starts.append(less_l_all[rank][k])                       # tie class starts after everything smaller
-        starts.append(less_l_all[rank][k] + eq_l_all[rank][k])   # next interior class
-    class_starts = starts[:2 * len(distinct) + 1]
-    return SplitPlan(total, targets, [int(x) for x in v_h], distinct, sizes, class_starts)
+    for u in distinct:                                                      # [interior_0][tie_0][interior_1][tie_1]...[interior_m]
+        k = values.index(u)
+        starts.append(less_l_all[rank][k])
+        starts.append(less_l_all[rank][k] + eq_l_all[rank][k])
+    return SplitPlan(total, targets, list(values), distinct, sizes, starts[:2 * len(distinct) + 1])
+
+
+def make_plan_exact(backend, keys: torch.Tensor, count: int, group=None) -> SplitPlan:
+    """Exact quantile splitters (multi-level histogram search): every rank receives N/G +- 1 keys."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    v, less_g, eq_g, less_l, eq_l, total, targets = find_splitters(backend, keys, count, group)
+    nb = world - 1
+    mine = torch.tensor([count] + less_l + eq_l, dtype=torch.int64, device=keys.device)
+    everyone = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(everyone, mine, group=group)
+    stats = torch.stack(everyone).cpu().tolist()
+    counts = [int(r[0]) for r in stats]
+    less_l_all = [[int(x) for x in r[1:1 + nb]] for r in stats]
+    eq_l_all = [[int(x) for x in r[1 + nb:1 + 2 * nb]] for r in stats]
+    return _plan_from_class_stats(world, rank, total, targets, v, less_g, eq_g, counts, less_l_all, eq_l_all)
+
+
+def make_plan_sampled(backend, keys: torch.Tensor, count: int, group=None) -> SplitPlan:
+    """Splitters from a sorted sample (SAMPLES_PER_RANK evenly strided keys per rank), then ONE exact
+    class-count pass over the local keys.  Counts are exact, so the result is exactly sorted and
+    tie classes are still cut exactly; only the balance is approximate (~1 % for uniform keys)."""
+    import numpy as np
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    device = keys.device
+    nb = world - 1
+    s_n = SAMPLES_PER_RANK
+    # every rank contributes the same number of samples (short ranks repeat / pad with their own keys)
+    if count > 0:
+        idx = (torch.arange(s_n, device=device, dtype=torch.int64) * count) // s_n
+        sample = keys[:count][idx].contiguous()
+        weight = torch.tensor([count], dtype=torch.int64, device=device)
+    else:
+        sample = torch.zeros(s_n, dtype=keys.dtype, device=device)
+        weight = torch.tensor([0], dtype=torch.int64, device=device)
+    gathered = [torch.empty_like(sample) for _ in range(world)]
+    dist.all_gather(gathered, sample, group=group)
+    weights = [torch.empty_like(weight) for _ in range(world)]
+    dist.all_gather(weights, weight, group=group)
+    counts = [int(w.item()) for w in weights]
+    total = sum(counts)
+    targets = [k * total // world for k in range(world + 1)]
+    if nb == 0 or total == 0:
+        return SplitPlan(total, targets, [], [], [[c if j == 0 else 0 for j in range(world)] for c in counts] if world == 1
+                         else [[0] * world for _ in range(world)], [0])
+    # weighted sample quantiles: a sample of rank s stands for counts[s] / s_n keys
+    pool = torch.cat([g for g, c in zip(gathered, counts) if c > 0])
+    wts = np.concatenate([np.full(s_n, c / s_n) for c in counts if c > 0])
+    u = (pool.to(torch.int64) & 0xFFFFFFFF).cpu().numpy()
+    order = np.argsort(u, kind="stable")
+    cum = np.cumsum(wts[order])
+    values = []
+    for k in range(1, world):
+        j = int(np.searchsorted(cum, targets[k], side="right"))
+        values.append(int(u[order[min(j, u.size - 1)]]))
+    distinct = sorted(set(values))
+    cls = backend.class_count(keys, count, _as_u32_tensor(distinct, device))
+    everyone = [torch.empty_like(cls) for _ in range(world)]
+    dist.all_gather(everyone, cls, group=group)
+    cls_all = torch.stack(everyone).cpu().numpy()                       # [world, 2m+1] exact local class sizes
+    excl = np.concatenate([np.zeros((world, 1), dtype=np.int64), np.cumsum(cls_all, axis=1)[:, :-1]], axis=1)
+    less_l_all, eq_l_all = [], []
+    for s in range(world):
+        less_l_all.append([int(excl[s, 2 * distinct.index(v) + 1]) for v in values])
+        eq_l_all.append([int(cls_all[s, 2 * distinct.index(v) + 1]) for v in values])
+    less_g = [sum(less_l_all[s][k] for s in range(world)) for k in range(nb)]
+    eq_g = [sum(eq_l_all[s][k] for s in range(world)) for k in range(nb)]
+    return _plan_from_class_stats(world, rank, total, targets, values, less_g, eq_g, counts, less_l_all, eq_l_all)
+
+
+def make_plan(backend, keys: torch.Tensor, count: int, group=None, strategy: str = "sampled") -> SplitPlan:
+    if strategy == "exact" or not hasattr(backend, "class_count"):
+        return make_plan_exact(backend, keys, count, group)
+    return make_plan_sampled(backend, keys, count, group)
 
 
 def distributed_sort(backend, keys: torch.Tensor, count: int | None = None, group=None, recv: torch.Tensor | None = None,
                      part: torch.Tensor | None = None, storage: torch.Tensor | None = None, timers=None,
-                     shared: "SharedReceive | None" = None):
+                     shared: "SharedReceive | None" = None, strategy: str = "sampled"):
     """Sort the union of every rank's keys[0:count].  Returns (recv_buffer, recv_count, plan): rank
     r's slice of the globally sorted sequence (global ranks [T_r, T_{r+1})).
 
@@ -278,7 +357,7 @@ def distributed_sort(backend, keys: torch.Tensor, count: int | None = None, grou
             timers.mark(name)
 
     mark("start")
-    plan = make_plan(backend, keys, n, group)
+    plan = make_plan(backend, keys, n, group, strategy)
     mark("splitters")
     in_splits = plan.sizes[rank]
     out_splits = [plan.sizes[s][rank] for s in range(world)]
