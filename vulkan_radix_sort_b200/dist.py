@@ -302,22 +302,19 @@ def make_plan_sampled(backend, keys: torch.Tensor, count: int, group=None) -> Sp
     dist.all_gather(gathered, sample, group=group)
     weights = [torch.empty_like(weight) for _ in range(world)]
     dist.all_gather(weights, weight, group=group)
-    counts = [int(w.item()) for w in weights]
+    counts = [int(x) for x in torch.cat(weights).cpu().tolist()]
     total = sum(counts)
     targets = [k * total // world for k in range(world + 1)]
     if nb == 0 or total == 0:
-        return SplitPlan(total, targets, [], [], [[c if j == 0 else 0 for j in range(world)] for c in counts] if world == 1
-                         else [[0] * world for _ in range(world)], [0])
-    # weighted sample quantiles: a sample of rank s stands for counts[s] / s_n keys
-    pool = torch.cat([g for g, c in zip(gathered, counts) if c > 0])
-    wts = np.concatenate([np.full(s_n, c / s_n) for c in counts if c > 0])
-    u = (pool.to(torch.int64) & 0xFFFFFFFF).cpu().numpy()
-    order = np.argsort(u, kind="stable")
-    cum = np.cumsum(wts[order])
-    values = []
-    for k in range(1, world):
-        j = int(np.searchsorted(cum, targets[k], side="right"))
-        values.append(int(u[order[min(j, u.size - 1)]]))
+        return SplitPlan(total, targets, [], [], [[counts[s] if j == 0 else 0 for j in range(world)] for s in range(world)], [0])
+    # weighted sample quantiles on the device: a sample of rank s stands for counts[s] / s_n keys
+    pool = torch.cat(gathered).to(torch.int64) & 0xFFFFFFFF
+    wts = torch.cat([torch.full((s_n,), c / s_n, dtype=torch.float64, device=device) for c in counts])
+    sorted_vals, order = torch.sort(pool)
+    cum = torch.cumsum(wts[order], dim=0)
+    want = torch.tensor(targets[1:world], dtype=torch.float64, device=device)
+    j = torch.searchsorted(cum, want, right=True).clamp(max=pool.numel() - 1)
+    values = [int(x) for x in sorted_vals[j].cpu().tolist()]
     distinct = sorted(set(values))
     cls = backend.class_count(keys, count, _as_u32_tensor(distinct, device))
     everyone = [torch.empty_like(cls) for _ in range(world)]
