@@ -51,7 +51,7 @@ def run(args, metric, unit):
     pristine = torch.from_numpy(host_keys.view(np.int32)).cuda()
     keys = torch.empty_like(pristine)
     backend = CudaBackend(local_rank)
-    strategy = os.environ.get("VRDX_DIST_SPLITTERS", "sampled")      # sampled: ~1 % imbalance; exact: N/G +- 1
+    strategy = os.environ.get("VRDX_DIST_SPLITTERS", "exact")        # exact: N/G +- 1 keys per rank; sampled: ~1 % imbalance
     cap = n + (n >> 4) + 1024
     fused = os.environ.get("VRDX_DIST_EXCHANGE", "fused") != "nccl"
     shared = SharedReceive(backend, cap) if fused else None

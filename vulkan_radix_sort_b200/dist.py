@@ -2,11 +2,12 @@
 
 BASELINE.json configs[4] / SURVEY.md §8(e).  The reference is single-device; this layer is new:
 
-  1. splitters.  Default ("sampled"): every rank contributes 2^16 evenly strided keys, the sorted
-     sample gives the G-1 splitter values, and ONE exact class-count pass over the local keys
-     (vrdxDistCmdClassCount, 4 B/key) gives every (rank, class) size.  Alternative ("exact"): a
-     3-level (8/12/12-bit) distributed histogram search finds the key value at every global rank
-     k*N/G (three 4 B/key passes); every rank then receives N/G +- 1 keys.  In both, ties on a
+  1. splitters.  Default ("exact"): a 3-level (8/12/12-bit) distributed histogram search finds the
+     key value at every global rank k*N/G (three 4 B/key passes over the local keys, three tiny
+     all-reduces); every rank then receives N/G +- 1 keys for ANY distribution.  Alternative
+     ("sampled"): every rank contributes 2^16 evenly strided keys, the sorted sample gives the
+     splitter values and ONE exact class-count pass (vrdxDistCmdClassCount) gives every (rank,
+     class) size; balance ~1 %.  Measured equal at 2 GPUs (host round trips dominate).  In both, ties on a
      splitter value (an all-equal input is one big tie) are cut exactly and handed out by source
      rank, which is legal for a keys-only sort because equal keys are indistinguishable;
   2. local multi-split (vrdxDistCmdPartition) into <= 2G-1 classes (open intervals between
@@ -330,7 +331,7 @@ def make_plan_sampled(backend, keys: torch.Tensor, count: int, group=None) -> Sp
     return _plan_from_class_stats(world, rank, total, targets, values, less_g, eq_g, counts, less_l_all, eq_l_all)
 
 
-def make_plan(backend, keys: torch.Tensor, count: int, group=None, strategy: str = "sampled") -> SplitPlan:
+def make_plan(backend, keys: torch.Tensor, count: int, group=None, strategy: str = "exact") -> SplitPlan:
     if strategy == "exact" or not hasattr(backend, "class_count"):
         return make_plan_exact(backend, keys, count, group)
     return make_plan_sampled(backend, keys, count, group)
@@ -338,7 +339,7 @@ def make_plan(backend, keys: torch.Tensor, count: int, group=None, strategy: str
 
 def distributed_sort(backend, keys: torch.Tensor, count: int | None = None, group=None, recv: torch.Tensor | None = None,
                      part: torch.Tensor | None = None, storage: torch.Tensor | None = None, timers=None,
-                     shared: "SharedReceive | None" = None, strategy: str = "sampled"):
+                     shared: "SharedReceive | None" = None, strategy: str = "exact"):
     """Sort the union of every rank's keys[0:count].  Returns (recv_buffer, recv_count, plan): rank
     r's slice of the globally sorted sequence (global ranks [T_r, T_{r+1})).
 
