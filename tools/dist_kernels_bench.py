@@ -19,7 +19,7 @@ def timeit(fn, reps=5):
 for world in (2, 8):
     nb = world - 1
     bounds = [(k + 1) * (1 << 32) // world for k in range(nb)]
-    for shift, bits in ((24, 8), (12, 12), (0, 12)):
+    for shift, bits in ((24, 8), (12, 12), (0, 12), (20, 12), (10, 10), (0, 10)):
         pref = torch.tensor([x >> (shift + bits) for x in bounds][: (1 if shift + bits == 32 else nb)], dtype=torch.int64, device="cuda")
         t = timeit(lambda: b.prefix_histogram(keys, n, shift, bits, pref))
         print(f"world={world} prefix_histogram shift={shift} bits={bits} P={pref.numel()}: {t:.3f} ms  {4*n/t/1e6:.0f} GB/s")

@@ -167,6 +167,10 @@ DistClassCountKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t spl
 // range per class with one global atomic (order between tiles is irrelevant for keys-only).
 constexpr int kDistPartThreads = 256;
 constexpr int kDistPartItems = 16;
+#ifndef VRDX_DIST_PART_MIN_CTAS
+#define VRDX_DIST_PART_MIN_CTAS 5
+#endif
+constexpr int kDistPartMinCtas = VRDX_DIST_PART_MIN_CTAS;
 constexpr int kDistPartTile = kDistPartThreads * kDistPartItems;
 constexpr int kDistClassSlots = 32;  // classes padded to a power of two
 
@@ -180,7 +184,7 @@ struct DistDestTable {
 };
 
 template <bool SCATTER>
-__global__ void __launch_bounds__(kDistPartThreads)
+__global__ void __launch_bounds__(kDistPartThreads, kDistPartMinCtas)
 DistPartitionKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t splitter_count,
                     const uint32_t* __restrict__ splitters, uint32_t* __restrict__ cursors,
                     uint32_t* __restrict__ out, uint32_t dest_count,

@@ -2,7 +2,7 @@
 
 BASELINE.json configs[4] / SURVEY.md §8(e).  The reference is single-device; this layer is new:
 
-  1. splitters.  Default ("exact"): a 3-level (8/12/12-bit) distributed histogram search finds the
+  1. splitters.  Default ("exact"): a 3-level (12/10/10-bit) distributed histogram search finds the
      key value at every global rank k*N/G (three 4 B/key passes over the local keys, three tiny
      all-reduces); every rank then receives N/G +- 1 keys for ANY distribution.  Alternative
      ("sampled"): every rank contributes 2^16 evenly strided keys, the sorted sample gives the
@@ -34,9 +34,10 @@ import torch
 import torch.distributed as dist
 
 def search_levels(boundaries: int):
-    """(shift, bits) of each level of the splitter search: 8/12/12 bits while the per-prefix
-    histograms fit in shared memory (<= 7 boundaries), else four 8-bit levels."""
-    return ((24, 8), (12, 12), (0, 12)) if boundaries <= 7 else ((24, 8), (16, 8), (8, 8), (0, 8))
+    """(shift, bits) of each level of the splitter search: 12/10/10 bits.  The first level has a
+    single (empty) prefix, the later ones one prefix per boundary; 1024 bins x <= 11 prefixes stay
+    under 48 KB of shared memory, so the histogram kernel keeps 4 CTAs per SM."""
+    return ((20, 12), (10, 10), (0, 10))
 
 
 def _u32_as_i32(t: torch.Tensor) -> torch.Tensor:
