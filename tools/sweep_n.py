@@ -5,13 +5,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vulkan_radix_sort_b200 import Sorter, api
 from vulkan_radix_sort_b200.datagen import make_keys
 res, pool = api.vrdxCudaCreateQueryPool(api.cuda_device(0), 15)
-sorters = {"onesweep": Sorter(0, algorithm=1), "rts": Sorter(0, algorithm=2), "auto": Sorter(0)}
+sorters = {"onesweep": Sorter(0, algorithm=1), "rts": Sorter(0, algorithm=2)}
 host = torch.from_numpy(make_keys("uniform", 1 << 28, 1).view(np.int32))
 src_all = host.cuda()
 vals_all = torch.arange(1 << 28, dtype=torch.int32, device="cuda")
-for log2n in range(18, 29):
-    n = 1 << log2n
-    line = f"2^{log2n}"
+import math
+for n in [1 << 18, 1 << 20, 1 << 21, 3 << 20, 1 << 22, 3 << 21, 1 << 23, 3 << 22, 1 << 24, 3 << 23, 1 << 25, 1 << 26]:
+    line = f"{n:9d} (2^{math.log2(n):.2f})"
     for kv in (False, True):
         for name, s in sorters.items():
             keys = torch.empty(n, dtype=torch.int32, device="cuda"); vals = torch.empty_like(keys)

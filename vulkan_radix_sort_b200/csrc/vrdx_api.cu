@@ -188,7 +188,8 @@ constexpr int kNumPairTmaVariants = sizeof(kPairTmaVariants) / sizeof(kPairTmaVa
 // Smallest tile of any compiled variant: sizes the look-back buffers whichever variant runs.
 constexpr uint32_t kMinTile = 4096;  // 256 x 16
 // AUTO: reduce-then-scan at and above this count, onesweep (fewer launches) below it.
-constexpr uint32_t kAutoRtsThreshold = 3u << 23;  // measured crossover between 2^24 and 2^25 (profiles/r01_sweep_n.txt)
+constexpr uint32_t kAutoRtsThresholdKeys = 3u << 23;   // measured crossovers (profiles/r01_sweep_n_final.txt):
+constexpr uint32_t kAutoRtsThresholdPairs = 3u << 24;  // keys-only ~2^24.6, key-value ~2^25.6
 
 struct VrdxSorter_T {
   int device = 0;
@@ -310,7 +311,8 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
   // 30-bit look-back cells: counts of 2^30 and above take the reduce-then-scan path (32-bit counts).
   const bool use_rts = sorter->algorithm == VRDX_CUDA_ALGORITHM_REDUCE_THEN_SCAN ||
                        (uint64_t)n_or_max >= kMaxOnesweepCount ||
-                       (sorter->algorithm == VRDX_CUDA_ALGORITHM_AUTO && n_or_max >= kAutoRtsThreshold);
+                       (sorter->algorithm == VRDX_CUDA_ALGORITHM_AUTO &&
+                        n_or_max >= (kv ? kAutoRtsThresholdPairs : kAutoRtsThresholdKeys));
 
   const StorageLayout lay = ComputeLayout(n_or_max, kMinTile);
   StorageHeader* hdr = reinterpret_cast<StorageHeader*>(storage + lay.header_offset);
