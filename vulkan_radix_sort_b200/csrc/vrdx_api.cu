@@ -188,6 +188,8 @@ constexpr int kNumPairTmaVariants = sizeof(kPairTmaVariants) / sizeof(kPairTmaVa
 // Smallest tile of any compiled variant: sizes the look-back buffers whichever variant runs.
 constexpr uint32_t kMinTile = 4096;  // 256 x 16
 // AUTO: reduce-then-scan at and above this count, onesweep (fewer launches) below it.
+// the conflict-free histogram kernel needs enough keys to fill one 1024-thread CTA per SM
+static uint32_t kHistPrivMinCount = 1u << 21;
 constexpr uint32_t kAutoRtsThresholdKeys = 3u << 23;   // measured crossovers (profiles/r01_sweep_n_final.txt):
 constexpr uint32_t kAutoRtsThresholdPairs = 3u << 24;  // keys-only ~2^24.6, key-value ~2^25.6
 
@@ -345,11 +347,19 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
                                       lay.status_a_offset + (uint64_t)tiles * kRadix * sizeof(uint32_t),
                                       stream));
     ++launches;
-    uint64_t chunks = CeilDiv(n_or_max, (uint64_t)kHistChunk);
-    uint64_t cap = (uint64_t)sorter->sm_count * 4;
-    uint32_t grid = (uint32_t)(chunks < cap ? (chunks ? chunks : 1) : cap);
-    NoteError(sorter, LaunchEx(HistogramKernel, grid, kHistThreads, 0, stream, false, (const uint32_t*)keys, indirect,
-                               n_or_max, hdr, st.Written(1)));
+    if (n_or_max >= kHistPrivMinCount) {
+      // lane-private (conflict-free) bins, one 1024-thread CTA per SM
+      uint64_t chunks = CeilDiv(n_or_max, (uint64_t)kHistPrivChunk);
+      uint32_t grid = (uint32_t)(chunks < (uint64_t)sorter->sm_count ? chunks : (uint64_t)sorter->sm_count);
+      NoteError(sorter, LaunchEx(HistogramKernelPrivate, grid, kHistPrivThreads, kHistPrivSmemBytes, stream, false,
+                                 (const uint32_t*)keys, indirect, n_or_max, hdr, st.Written(1)));
+    } else {
+      uint64_t chunks = CeilDiv(n_or_max, (uint64_t)kHistChunk);
+      uint64_t cap = (uint64_t)sorter->sm_count * 4;
+      uint32_t grid = (uint32_t)(chunks < cap ? (chunks ? chunks : 1) : cap);
+      NoteError(sorter, LaunchEx(HistogramKernel, grid, kHistThreads, 0, stream, false, (const uint32_t*)keys, indirect,
+                                 n_or_max, hdr, st.Written(1)));
+    }
     ++launches;
   } else {
     st.Same(1);  // reduce-then-scan keeps no state across passes: every table it reads is written first
@@ -485,6 +495,13 @@ VkResult vrdxCudaCreateSorter(const VrdxSorterCreateInfo* pCreateInfo,
   s->tile_load = tile_load;
   if (const char* e = getenv("VRDX_ALGORITHM")) s->algorithm = (VrdxCudaAlgorithm)atoi(e);
   if (const char* e = getenv("VRDX_PDL")) g_pdl = atoi(e) != 0;
+  if (const char* e = getenv("VRDX_HIST_PRIVATE_MIN")) kHistPrivMinCount = (uint32_t)strtoul(e, nullptr, 10);
+  if (cudaFuncSetAttribute(HistogramKernelPrivate, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)kHistPrivSmemBytes) != cudaSuccess) {
+    cudaGetLastError();
+    delete s;
+    return VK_ERROR_INITIALIZATION_FAILED;
+  }
   if (pOptions && pOptions->structSize >= sizeof(VrdxCudaSorterOptions) &&
       pOptions->algorithm != VRDX_CUDA_ALGORITHM_AUTO)
     s->algorithm = pOptions->algorithm;

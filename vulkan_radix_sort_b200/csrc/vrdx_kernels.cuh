@@ -179,6 +179,100 @@ HistogramKernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ 
   }
 }
 
+// HistogramKernelPrivate — the same contract as HistogramKernel, for larger inputs: every bin has 32
+// lane-private copies laid out as bin*32 + lane, so the bank of a shared-memory atomic is the
+// lane id and no two lanes of a warp ever conflict, whatever the digits (HistogramKernel spends
+// 13 cycles per 32 keys on 4 conflicting atomics, profiles/r01_microbench_rank.txt; here 4).
+// 4 x 256 x 32 counters = 128 KB of shared memory: one 1024-thread CTA per SM, grid-stride.
+constexpr int kHistPrivThreads = 1024;
+constexpr int kHistPrivChunk = kHistPrivThreads * kHistVecPerThread * 4;  // keys per CTA per iteration
+constexpr size_t kHistPrivSmemBytes = (size_t)kPasses * kRadix * 32 * sizeof(uint32_t);
+
+__device__ __forceinline__ void HistCountPrivate(uint32_t* sh, uint32_t lane, uint32_t k) {
+  atomicAdd(&sh[((0 * kRadix + (k & 0xFFu)) << 5) + lane], 1u);
+  atomicAdd(&sh[((1 * kRadix + ((k >> 8) & 0xFFu)) << 5) + lane], 1u);
+  atomicAdd(&sh[((2 * kRadix + ((k >> 16) & 0xFFu)) << 5) + lane], 1u);
+  atomicAdd(&sh[((3 * kRadix + (k >> 24)) << 5) + lane], 1u);
+}
+
+__global__ void __launch_bounds__(kHistPrivThreads, 1)
+HistogramKernelPrivate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ indirect,
+                       uint32_t n_or_max, StorageHeader* __restrict__ hdr, unsigned long long* ts_end) {
+  extern __shared__ __align__(16) uint32_t sh[];  // [4][256][32]
+  __shared__ uint32_t s_last;
+  const int tid = threadIdx.x;
+  const uint32_t lane = tid & 31;
+  GridDepLaunch();
+  const uint32_t n = ResolveCount(indirect, n_or_max);
+  {
+    uint4* z = reinterpret_cast<uint4*>(sh);
+#pragma unroll
+    for (int j = 0; j < (int)(kPasses * kRadix * 32 / 4 / kHistPrivThreads); ++j)
+      z[j * kHistPrivThreads + tid] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (blockIdx.x == 0 && tid == 0) hdr->element_count[0] = n;
+  __syncthreads();
+
+  const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(keys) >> 2) & 3u);
+  uint32_t head = mis ? 4u - mis : 0u;
+  if (head > n) head = n;
+  const uint4* __restrict__ body = reinterpret_cast<const uint4*>(keys + head);
+  const uint64_t nvec = (uint64_t)(n - head) >> 2;
+  const uint32_t tail_start = head + (uint32_t)(nvec << 2);
+  constexpr uint64_t kVecPerChunk = (uint64_t)kHistPrivThreads * kHistVecPerThread;
+  for (uint64_t base = (uint64_t)blockIdx.x * kVecPerChunk; base < nvec; base += (uint64_t)gridDim.x * kVecPerChunk) {
+    uint4 v[kHistVecPerThread];
+#pragma unroll
+    for (int j = 0; j < kHistVecPerThread; ++j) {
+      const uint64_t idx = base + (uint64_t)j * kHistPrivThreads + tid;
+      v[j] = idx < nvec ? __ldcs(body + idx) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int j = 0; j < kHistVecPerThread; ++j) {
+      if (base + (uint64_t)j * kHistPrivThreads + tid < nvec) {
+        HistCountPrivate(sh, lane, v[j].x); HistCountPrivate(sh, lane, v[j].y);
+        HistCountPrivate(sh, lane, v[j].z); HistCountPrivate(sh, lane, v[j].w);
+      }
+    }
+  }
+  if (blockIdx.x == 0) {  // unaligned head (< 4 keys) and the n % 4 tail
+    if ((uint32_t)tid < head) HistCountPrivate(sh, lane, keys[tid]);
+    const uint32_t t = tail_start + tid;
+    if (tid < 4 && t < n) HistCountPrivate(sh, lane, keys[t]);
+  }
+  __syncthreads();
+
+  // one bin per thread: sum its 32 lane copies (rotated start, so the 32 threads of a warp read
+  // 32 different banks), then one global atomic per non-empty bin
+  uint32_t* gh = &hdr->global_hist[0][0];
+  {
+    uint32_t c = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) c += sh[(tid << 5) + ((lane + j) & 31)];
+    if (c) atomicAdd(gh + tid, c);
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&hdr->hist_blocks_done, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  StampEnd(ts_end);
+  const int warp = tid >> 5;
+  if (warp < kPasses) {
+    uint32_t* h = gh + warp * kRadix + lane * 8;
+    uint32_t c[8], sum = 0;
+    bool all_in_one = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { c[j] = __ldcg(h + j); sum += c[j]; all_in_one |= (c[j] == n); }
+    uint32_t excl = WarpInclusiveScan(sum, lane) - sum;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { h[j] = excl; excl += c[j]; }
+    const uint32_t any = __ballot_sync(0xffffffffu, all_in_one && n != 0);
+    if (lane == 0) hdr->pass_identity[warp] = any ? 1u : 0u;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // OnesweepKernel — one LSD pass over one tile per CTA.
 // Algorithmic traffic per pass: 4 B/key read + 4 B/key write (+ 4 + 4 for values).
