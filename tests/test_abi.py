@@ -103,3 +103,50 @@ def test_no_cpu_fallback_in_product_package():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "cpu_oracle" not in text and "liboracle" not in text and "lsd_oracle" not in text, f
+
+
+def _prototypes(header):
+    """name -> list of C parameter type strings, parsed from a header of this repo."""
+    text = open(os.path.join(INCLUDE, header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    protos = {}
+    for m in re.finditer(r"\b(vrdx[A-Za-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        name, params = m.group(1), m.group(2).strip()
+        parts = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        protos[name] = parts
+    return protos
+
+
+def _ctype_kind(c_param: str) -> str:
+    """Coarse ABI class of a C parameter: 'ptr', 'u64', 'u32' or 'i32'."""
+    t = c_param.rsplit(" ", 1)[0] if " " in c_param else c_param
+    if "*" in c_param or "[" in c_param:
+        return "ptr"
+    if t in ("VkBuffer", "VkCommandBuffer", "VkDevice", "VkPhysicalDevice", "VkQueryPool", "VkPipelineCache",
+             "VrdxSorter", "VrdxCudaImportedMemory"):
+        return "ptr"   # dispatchable and non-dispatchable handles are pointers on 64-bit
+    if t in ("VkDeviceSize", "uint64_t", "size_t"):
+        return "u64"
+    if t in ("uint32_t",):
+        return "u32"
+    if t in ("int",):
+        return "i32"
+    raise AssertionError(f"unclassified C parameter type: {c_param!r}")
+
+
+def test_ctypes_signatures_match_the_c_prototypes():
+    """Every exported function: same parameter count and ABI class in include/*.h and in api._SIGNATURES."""
+    kinds = {ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr", ctypes.c_uint64: "u64", ctypes.c_uint32: "u32",
+             ctypes.c_int: "i32"}
+    protos = {}
+    for h in ("vk_radix_sort.h", "vrdx_cuda.h", "vrdx_dist.h"):
+        protos.update(_prototypes(h))
+    for name, (restype, argtypes) in api._SIGNATURES.items():
+        assert name in protos, name
+        c_params = protos[name]
+        assert len(c_params) == len(argtypes), (name, c_params, argtypes)
+        for c_param, a in zip(c_params, argtypes):
+            want = _ctype_kind(c_param)
+            got = "ptr" if hasattr(a, "contents") or a in (ctypes.c_void_p, ctypes.c_char_p) else kinds[a]
+            assert want == got, (name, c_param, a)
