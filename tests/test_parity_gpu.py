@@ -282,6 +282,35 @@ def test_query_pool_timestamps(sorter):
     api.vrdxCudaDestroyQueryPool(pool)
 
 
+def test_query_pool_inside_cuda_graph(any_sorter, oracle):
+    # GPU-written timestamps are ordinary kernel work, so they can be captured and replayed
+    sorter = any_sorter
+    n = (1 << 20) + 3
+    k, _ = DataGenerator(9).generate(n)
+    dk = to_dev(k)
+    storage = torch.empty(sorter.storage_requirements(n).size, dtype=torch.uint8, device=DEV)
+    res, pool = api.vrdxCudaCreateQueryPool(api.cuda_device(0), 2 * api.QUERY_COUNT)
+    assert res == api.VK_SUCCESS
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            sorter.sort(dk, storage=storage, stream=s, query_pool=pool, query=api.QUERY_COUNT)  # second half of the pool
+    torch.cuda.synchronize()
+    for rep in range(2):
+        dk.copy_(to_dev(k))
+        g.replay()
+        torch.cuda.synchronize()
+        assert np.array_equal(to_np(dk), oracle.sort_keys(k))
+        res, ts = api.vrdxCudaGetQueryPoolResults(pool, api.QUERY_COUNT, api.QUERY_COUNT)
+        assert res == api.VK_SUCCESS
+        assert ts[0] == 0 and ts[14] > 0 and all(b >= a for a, b in zip(ts, ts[1:]))
+    res, _ = api.vrdxCudaGetQueryPoolResults(pool, 0, api.QUERY_COUNT)
+    assert res == api.VK_NOT_READY  # the first half of the pool was never written
+    api.vrdxCudaDestroyQueryPool(pool)
+
+
 def test_errors_are_sticky_not_fatal(sorter):
     api.vrdxCmdSort(None, sorter.handle, 16, None, 0, None, 0, None, 0)  # NULL buffers
     assert api.vrdxCudaGetLastError(sorter.handle) != 0
