@@ -15,7 +15,8 @@ REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(REPO_ROOT, "include")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libvrdx_b200.so")
+# VRDX_LIB: developer override (A/B builds of the same ABI); the default is the in-tree product library
+LIB_PATH = os.environ.get("VRDX_LIB") or os.path.join(LIB_DIR, "libvrdx_b200.so")
 
 SOURCES = ["vrdx_api.cu"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -367,21 +367,49 @@ __device__ __forceinline__ uint32_t WarpRankDigit(uint32_t* cnt, uint32_t d, uin
 // in flight per round trip; `look_s` holds the first batch (tiles tile-1 .. tile-kLookBatch),
 // already loaded by the caller.  Cells are consumed strictly nearest-first and the walk stops at
 // the first inclusive prefix (tile 0 always publishes one, so the walk never underflows).
+#ifndef VRDX_LOOK_WIDE
+#define VRDX_LOOK_WIDE 4  // cells per round trip after the first (prefetched) batch; 12 and 24 measured slower
+#endif
 template <int kLookBatch>
 __device__ __forceinline__ uint32_t LookBack(const uint32_t* status, uint32_t tile, int digit,
                                              uint32_t (&look_s)[kLookBatch], uint32_t* stats = nullptr) {
+  constexpr int kWide = VRDX_LOOK_WIDE > kLookBatch ? VRDX_LOOK_WIDE : kLookBatch;
   uint32_t excl = 0;
   uint32_t look = tile - 1;  // nearest tile not yet consumed
   bool done = false;
 #ifdef VRDX_STATS
   uint32_t st_rounds = 1, st_cells = 0, st_notready = 0;
 #endif
-  while (!done) {
+  // first batch: the cells prefetched by the caller before the reorder
 #pragma unroll
-    for (int j = 0; j < kLookBatch; ++j) {
+  for (int j = 0; j < kLookBatch; ++j) {
+    if (done) break;
+    const uint32_t s = look_s[j];
+    if ((s >> 30) == 0u) break;  // not published yet: re-poll from `look`
+    excl += s & kStatusValueMask;
+#ifdef VRDX_STATS
+    ++st_cells;
+#endif
+    if (s & kStatusPrefix) { done = true; break; }
+    --look;
+  }
+  // later rounds: the walk is ~20 cells deep at full speed (profiles/r01_lookback_depth_stats.txt),
+  // so fetch a wider window per round trip; cells are still consumed strictly nearest-first
+  while (!done) {
+#ifdef VRDX_STATS
+    ++st_rounds;
+#endif
+    uint32_t w[kWide];
+#pragma unroll
+    for (int j = 0; j < kWide; ++j) {
+      const uint32_t t = (look >= (uint32_t)j) ? look - j : 0u;
+      w[j] = LdRelaxed(status + (size_t)t * kRadix + digit);
+    }
+#pragma unroll
+    for (int j = 0; j < kWide; ++j) {
       if (done) break;
-      const uint32_t s = look_s[j];
-      if ((s >> 30) == 0u) {  // not published yet: re-poll from `look`
+      const uint32_t s = w[j];
+      if ((s >> 30) == 0u) {
 #ifdef VRDX_STATS
         ++st_notready;
 #endif
@@ -393,16 +421,6 @@ __device__ __forceinline__ uint32_t LookBack(const uint32_t* status, uint32_t ti
 #endif
       if (s & kStatusPrefix) { done = true; break; }
       --look;
-    }
-    if (!done) {
-#ifdef VRDX_STATS
-      ++st_rounds;
-#endif
-#pragma unroll
-      for (int j = 0; j < kLookBatch; ++j) {
-        const uint32_t t = (look >= (uint32_t)j) ? look - j : 0u;
-        look_s[j] = LdRelaxed(status + (size_t)t * kRadix + digit);
-      }
     }
   }
 #ifdef VRDX_STATS
