@@ -48,6 +48,7 @@ struct PassVariant {
 };
 
 // Launch with (or without) the programmatic-dependent-launch attribute; see GridDepWait().
+// Process-wide developer switch (VRDX_PDL=0), read once per sorter creation; not sort state.
 static bool g_pdl = true;
 template <typename... KArgs, typename... Args>
 cudaError_t LaunchEx(void (*kernel)(KArgs...), uint32_t grid, uint32_t block, size_t smem, cudaStream_t stream,
@@ -189,7 +190,7 @@ constexpr int kNumPairTmaVariants = sizeof(kPairTmaVariants) / sizeof(kPairTmaVa
 constexpr uint32_t kMinTile = 4096;  // 256 x 16
 // AUTO: reduce-then-scan at and above this count, onesweep (fewer launches) below it.
 // the conflict-free histogram kernel needs enough keys to fill one 1024-thread CTA per SM
-static uint32_t kHistPrivMinCount = 1u << 21;
+static uint32_t g_hist_private_min_count = 1u << 21;  // developer override: VRDX_HIST_PRIVATE_MIN
 constexpr uint32_t kAutoRtsThresholdKeys = 3u << 23;   // measured crossovers (profiles/r01_sweep_n_final.txt):
 constexpr uint32_t kAutoRtsThresholdPairs = 3u << 24;  // keys-only ~2^24.6, key-value ~2^25.6
 
@@ -347,7 +348,7 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
                                       lay.status_a_offset + (uint64_t)tiles * kRadix * sizeof(uint32_t),
                                       stream));
     ++launches;
-    if (n_or_max >= kHistPrivMinCount) {
+    if (n_or_max >= g_hist_private_min_count) {
       // lane-private (conflict-free) bins, one 1024-thread CTA per SM
       uint64_t chunks = CeilDiv(n_or_max, (uint64_t)kHistPrivChunk);
       uint32_t grid = (uint32_t)(chunks < (uint64_t)sorter->sm_count ? chunks : (uint64_t)sorter->sm_count);
@@ -495,7 +496,7 @@ VkResult vrdxCudaCreateSorter(const VrdxSorterCreateInfo* pCreateInfo,
   s->tile_load = tile_load;
   if (const char* e = getenv("VRDX_ALGORITHM")) s->algorithm = (VrdxCudaAlgorithm)atoi(e);
   if (const char* e = getenv("VRDX_PDL")) g_pdl = atoi(e) != 0;
-  if (const char* e = getenv("VRDX_HIST_PRIVATE_MIN")) kHistPrivMinCount = (uint32_t)strtoul(e, nullptr, 10);
+  if (const char* e = getenv("VRDX_HIST_PRIVATE_MIN")) g_hist_private_min_count = (uint32_t)strtoul(e, nullptr, 10);
   if (cudaFuncSetAttribute(HistogramKernelPrivate, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)kHistPrivSmemBytes) != cudaSuccess) {
     cudaGetLastError();
