@@ -526,9 +526,18 @@ OnesweepKernel(const PassArgs a) {
   {
     uint32_t* cnt = s_cnt + warp * kRadix;
     const uint32_t lt = LaneMaskLt();
+    if (!KV && a.pass == 0) {
+      // Keys-only, first pass: there is no earlier order to preserve and equal keys are
+      // indistinguishable, so ANY bijective ranking inside a digit gives the same final output.
+      // The value returned by the atomic is such a ranking: no read-back, no collision repair.
+      // (Every later pass, and every pass of a key-value sort, must be stable.)
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      rank[i] = WarpRankDigit(cnt, (key[i] >> shift) & 0xFFu, lt);
+      for (int i = 0; i < IPT; ++i) rank[i] = atomicAdd(&cnt[(key[i] >> shift) & 0xFFu], 1u);
+    } else {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        rank[i] = WarpRankDigit(cnt, (key[i] >> shift) & 0xFFu, lt);
+      }
     }
   }
   __syncthreads();
