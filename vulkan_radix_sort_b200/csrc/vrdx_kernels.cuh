@@ -470,10 +470,13 @@ OnesweepKernel(const PassArgs a) {
   GridDepWait();  // everything below reads what the previous kernel of this sort wrote
   // Tile ids are handed out in arrival order so that every predecessor a tile may wait on in
   // the look-back is already resident (forward progress without relying on blockIdx order).
-  if (MODE == 0 && tid == 0) s_misc[8] = atomicAdd(&a.hdr->tickets[a.pass], 1u);  // MODE 1/2: blockIdx.x
+  // Keys-only onesweep pass 0 is order-free (see the ranking below): tiles claim their output
+  // ranges with global atomics, so it needs neither tickets nor the look-back chain.
+  const bool unordered = (MODE != 1) && !KV && a.pass == 0;
+  if (MODE == 0 && !unordered && tid == 0) s_misc[8] = atomicAdd(&a.hdr->tickets[a.pass], 1u);  // MODE 1/2: blockIdx.x
   __syncthreads();
 
-  const uint32_t tile = (MODE == 0) ? s_misc[8] : blockIdx.x;
+  const uint32_t tile = (MODE == 0 && !unordered) ? s_misc[8] : blockIdx.x;
   const uint64_t tile_start = (uint64_t)tile * kTile;
   if (tile_start >= n) return;  // indirect count below max: surplus CTAs retire (upsweep.slang:20-22)
   const uint32_t remaining = (uint32_t)(n - tile_start);
@@ -554,7 +557,7 @@ OnesweepKernel(const PassArgs a) {
     }
     // pads were counted as digit 255; they are not part of the data
     digit_count = sum - ((tid == kRadix - 1) ? ((uint32_t)kTile - tile_count) : 0u);
-    if (MODE != 1)
+    if (MODE != 1 && !unordered)
       StRelaxed(a.status + (size_t)tile * kRadix + tid,
                 (tile == 0 ? kStatusPrefix : kStatusAggregate) | digit_count);
     const uint32_t incl = WarpInclusiveScan(sum, lane);
@@ -574,7 +577,10 @@ OnesweepKernel(const PassArgs a) {
       run += wcount[w];
     }
     // start the first batch of look-back loads now; it is consumed after the reorder below
-    if (MODE != 1) {
+    if (unordered) {
+      // claim [excl, excl + digit_count) of this digit's global run; the round trip overlaps the reorder
+      look_s[0] = digit_count ? atomicAdd(&a.hdr->claim_cursor[tid], digit_count) : 0u;
+    } else if (MODE != 1) {
 #pragma unroll
       for (int j = 0; j < kLookBatch; ++j) {
         const uint32_t t = (tile > (uint32_t)j) ? tile - 1 - j : 0u;
@@ -628,13 +634,11 @@ OnesweepKernel(const PassArgs a) {
   // order (nearest tile first) and the walk stops at the first inclusive prefix.
   if (tid < kRadix) {
     uint32_t excl = 0;
-    if (MODE != 1) {
-      if (tile > 0) {
-        excl = LookBack<kLookBatch>(a.status, tile, tid, look_s, a.hdr->reserved);
-        StRelaxed(a.status + (size_t)tile * kRadix + tid, kStatusPrefix | (excl + digit_count));
-      }
-    } else {
+    if (unordered || MODE == 1) {
       excl = look_s[0];
+    } else if (tile > 0) {
+      excl = LookBack<kLookBatch>(a.status, tile, tid, look_s, a.hdr->reserved);
+      StRelaxed(a.status + (size_t)tile * kRadix + tid, kStatusPrefix | (excl + digit_count));
     }
     // global slot of tile-local slot 0 for this digit (mod 2^32 arithmetic)
     s_gbase[tid] = a.hdr->global_hist[a.pass][tid] + excl - digit_excl;

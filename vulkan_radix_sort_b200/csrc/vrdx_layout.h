@@ -31,6 +31,7 @@ struct alignas(16) StorageHeader {
   uint32_t hist_blocks_done;              // last-block-done counter of the histogram / spine kernels
   uint32_t reserved[3];
   uint32_t pass_identity[kPasses];        // 1: every key holds the same digit in this pass -> the pass is a copy
+  uint32_t claim_cursor[kRadix];          // keys-only onesweep pass 0: per-digit output cursor tiles claim space from
 };
 static_assert(sizeof(StorageHeader) % 16 == 0, "header must keep 16-byte alignment");
 
