@@ -16,7 +16,11 @@ for name in only:
             dk = torch.from_numpy(k.view(np.int32)).cuda()
             dv = torch.arange(n, dtype=torch.int32, device="cuda")
             cnt = torch.tensor([max(n - 5, 0)], dtype=torch.int32, device="cuda")
-            s.sort(dk.clone())
+            kk = dk.clone()
+            s.sort(kk)
+            assert np.array_equal(kk.cpu().numpy().view(np.uint32), np.sort(k)), (name, n, dist, 'keys')
+            kk = dk.clone()
+            s.sort_indirect(kk, cnt, max_count=n)
             s.sort_key_value_indirect(dk, dv, cnt, max_count=n)
             torch.cuda.synchronize()
             c = int(cnt.item())
