@@ -39,7 +39,7 @@ static inline VkCommandBuffer vrdxCudaCommandBuffer(void* cudaStream) {
 /* ------------------------------------------------------------------ creation options */
 
 typedef enum VrdxCudaAlgorithm {
-  VRDX_CUDA_ALGORITHM_AUTO = 0,             /* onesweep; reduce-then-scan when N >= 2^30 */
+  VRDX_CUDA_ALGORITHM_AUTO = 0,             /* onesweep below 3*2^23 keys (3*2^24 pairs), reduce-then-scan from there up */
   VRDX_CUDA_ALGORITHM_ONESWEEP = 1,         /* histogram + 4 single-pass (decoupled look-back) kernels */
   VRDX_CUDA_ALGORITHM_REDUCE_THEN_SCAN = 2  /* per pass: tile histogram, spine scan, scatter (the reference's shape) */
 } VrdxCudaAlgorithm;
@@ -60,6 +60,47 @@ typedef struct VrdxCudaSorterOptions {
 /* vrdxCreateSorter with explicit options (NULL options == vrdxCreateSorter). */
 VkResult vrdxCudaCreateSorter(const VrdxSorterCreateInfo* pCreateInfo,
                               const VrdxCudaSorterOptions* pOptions, VrdxSorter* pSorter);
+
+/* ------------------------------------------------------------------ key types, order, bit range
+ *
+ * Absent from the reference (CUB exposes the same knobs,
+ * bench/cuda_benchmark.cu:63).  The eight vrdxCmdSort* entry points are unchanged: uint32 keys,
+ * ascending, all 32 bits.  vrdxCudaCmdSortEx is the general form. */
+
+typedef enum VrdxCudaKeyType {
+  VRDX_CUDA_KEY_TYPE_UINT32 = 0,
+  VRDX_CUDA_KEY_TYPE_INT32 = 1,   /* two's complement, negative before positive */
+  VRDX_CUDA_KEY_TYPE_FLOAT32 = 2  /* IEEE-754 total order of the bit patterns: -NaN < -inf < ... < -0 < +0 < ... < +inf < +NaN */
+} VrdxCudaKeyType;
+
+typedef enum VrdxCudaSortOrder {
+  VRDX_CUDA_SORT_ORDER_ASCENDING = 0,
+  VRDX_CUDA_SORT_ORDER_DESCENDING = 1 /* still stable: equal keys keep their input order */
+} VrdxCudaSortOrder;
+
+typedef struct VrdxCudaSortKeyInfo {
+  uint32_t structSize; /* = sizeof(VrdxCudaSortKeyInfo) */
+  VrdxCudaKeyType keyType;
+  VrdxCudaSortOrder order;
+  /* Only bits [beginBit, endBit) of the key take part in the comparison (bit positions of the
+   * order-preserving unsigned image of the key, as in CUB); elements equal in that range keep
+   * their input order.  0 <= beginBit <= endBit <= 32.  ceil((endBit-beginBit)/8) passes run
+   * instead of 4; an empty range is a no-op. */
+  uint32_t beginBit;
+  uint32_t endBit;
+  uint32_t reserved[3]; /* zero */
+} VrdxCudaSortKeyInfo;
+
+/* General sort.  pKeyInfo NULL = uint32 / ascending / bits [0,32).  indirectBuffer NULL = direct
+ * (elementCount is the count), else elementCount is maxElementCount and the uint32 count is read
+ * on the device (clamped).  valuesBuffer NULL = keys only.  Storage as for vrdxCmdSort* (size it
+ * with vrdxGetSorter[KeyValue]StorageRequirements).  Same stream, timestamp and error rules. */
+void vrdxCudaCmdSortEx(VkCommandBuffer commandBuffer, VrdxSorter sorter,
+                       const VrdxCudaSortKeyInfo* pKeyInfo, uint32_t elementCount,
+                       VkBuffer indirectBuffer, VkDeviceSize indirectOffset, VkBuffer keysBuffer,
+                       VkDeviceSize keysOffset, VkBuffer valuesBuffer, VkDeviceSize valuesOffset,
+                       VkBuffer storageBuffer, VkDeviceSize storageOffset, VkQueryPool queryPool,
+                       uint32_t query);
 
 /* ------------------------------------------------------------------ error channel */
 
@@ -95,6 +136,21 @@ VkResult vrdxCudaImportMemoryFd(VkDevice device, int fd, VkDeviceSize allocation
                                 int dedicated, VrdxCudaImportedMemory* pMemory);
 VkBuffer vrdxCudaImportedMemoryBuffer(VrdxCudaImportedMemory memory, VkDeviceSize memoryOffset);
 void vrdxCudaReleaseImportedMemory(VrdxCudaImportedMemory memory);
+
+/* Import a VkSemaphore a Vulkan application exported as an opaque POSIX fd
+ * (VK_KHR_external_semaphore_fd; `timeline` non-zero for a VK_SEMAPHORE_TYPE_TIMELINE one), and
+ * wait for / signal it in stream order: the Vulkan queue signals `value`, the sort's stream waits
+ * for it, sorts, and signals the value the Vulkan side waits for — the reference's barrier
+ * contract (README.md:150-157) across the two APIs.  `value` is ignored for binary semaphores.
+ * On success CUDA owns the fd. */
+typedef struct VrdxCudaImportedSemaphore_T* VrdxCudaImportedSemaphore;
+VkResult vrdxCudaImportSemaphoreFd(VkDevice device, int fd, int timeline,
+                                   VrdxCudaImportedSemaphore* pSemaphore);
+VkResult vrdxCudaCmdWaitSemaphore(VkCommandBuffer commandBuffer, VrdxCudaImportedSemaphore semaphore,
+                                  uint64_t value);
+VkResult vrdxCudaCmdSignalSemaphore(VkCommandBuffer commandBuffer, VrdxCudaImportedSemaphore semaphore,
+                                    uint64_t value);
+void vrdxCudaReleaseImportedSemaphore(VrdxCudaImportedSemaphore semaphore);
 
 /* ------------------------------------------------------------------ introspection */
 

@@ -119,6 +119,40 @@ def sort_partitioned(keys: np.ndarray, values, count: int):
     return k, None
 
 
+# ----------------------------------------------------------------- key-type / order / bit-range extension
+
+KEY_UINT32, KEY_INT32, KEY_FLOAT32 = 0, 1, 2
+
+
+def sortable_image(bits: np.ndarray, key_type: int = KEY_UINT32, descending: bool = False) -> np.ndarray:
+    """Order-preserving unsigned image of 32-bit keys given as raw uint32 bit patterns.
+
+    No counterpart in the reference; this is the definition the CUDA path
+    (include/vrdx_cuda.h: VrdxCudaSortKeyInfo) is checked against, and tests/test_oracle.py pins it
+    to NumPy's own typed sorts: int32 flips the sign bit, float32 flips all bits of negatives and the
+    sign bit of the rest (IEEE-754 total order), descending complements the image."""
+    b = np.ascontiguousarray(bits).view(np.uint32)
+    if key_type == KEY_INT32:
+        t = b ^ np.uint32(0x80000000)
+    elif key_type == KEY_FLOAT32:
+        neg = (b >> np.uint32(31)).astype(bool)
+        t = np.where(neg, ~b, b ^ np.uint32(0x80000000)).astype(np.uint32)
+    else:
+        t = b.copy()
+    return (~t).astype(np.uint32) if descending else t
+
+
+def sort_ex(bits: np.ndarray, values=None, key_type: int = KEY_UINT32, descending: bool = False,
+            begin_bit: int = 0, end_bit: int = 32):
+    """Stable sort by bits [begin_bit, end_bit) of the sortable image; returns (keys, values) as uint32."""
+    b = np.ascontiguousarray(bits).view(np.uint32)
+    assert 0 <= begin_bit <= end_bit <= 32
+    field = sortable_image(b, key_type, descending).astype(np.uint64) >> np.uint64(begin_bit)
+    field &= np.uint64((1 << (end_bit - begin_bit)) - 1)
+    perm = np.argsort(field, kind="stable")
+    return b[perm], (None if values is None else np.ascontiguousarray(values).view(np.uint32)[perm])
+
+
 def is_sorted(keys: np.ndarray) -> bool:
     k = np.ascontiguousarray(keys, dtype=np.uint32)
     return bool(oracle_lib().vrdx_oracle_is_sorted(_ptr(k), k.size))

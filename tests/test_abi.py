@@ -124,7 +124,7 @@ def _ctype_kind(c_param: str) -> str:
     if "*" in c_param or "[" in c_param:
         return "ptr"
     if t in ("VkBuffer", "VkCommandBuffer", "VkDevice", "VkPhysicalDevice", "VkQueryPool", "VkPipelineCache",
-             "VrdxSorter", "VrdxCudaImportedMemory"):
+             "VrdxSorter", "VrdxCudaImportedMemory", "VrdxCudaImportedSemaphore"):
         return "ptr"   # dispatchable and non-dispatchable handles are pointers on 64-bit
     if t in ("VkDeviceSize", "uint64_t", "size_t"):
         return "u64"

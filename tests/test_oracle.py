@@ -123,3 +123,60 @@ def test_oracle_against_live_reference(oracle):
         rkk, rkv, _ = oracle.ref_sort_key_value(k, v)
         ok, ov = oracle.sort_partitioned(k, v, k.size)
         assert np.array_equal(ok, rkk) and np.array_equal(ov, rkv), dist
+
+
+# ---- key-type / order / bit-range extension: the oracle's definition is pinned to NumPy's typed sorts
+
+def _special_floats(rng, n):
+    f = rng.standard_normal(n).astype(np.float32) * np.float32(1e3)
+    f[:: 17] = 0.0
+    f[1:: 19] = -0.0
+    f[2:: 23] = np.inf
+    f[3:: 29] = -np.inf
+    f[4:: 31] = np.float32(1e-42)      # subnormal
+    f[5:: 37] = np.float32(-1e-42)
+    return f
+
+
+def test_sort_ex_matches_numpy_typed_sorts(oracle):
+    rng = np.random.default_rng(11)
+    u = rng.integers(0, 1 << 32, 50_000, dtype=np.uint64).astype(np.uint32)
+    got, _ = oracle.sort_ex(u)
+    assert np.array_equal(got, np.sort(u)) and np.array_equal(got, oracle.sort_keys(u))
+    i = u.view(np.int32)
+    got, _ = oracle.sort_ex(i, key_type=oracle.KEY_INT32)
+    assert np.array_equal(got.view(np.int32), np.sort(i))
+    got, _ = oracle.sort_ex(i, key_type=oracle.KEY_INT32, descending=True)
+    assert np.array_equal(got.view(np.int32), np.sort(i)[::-1])
+    f = _special_floats(rng, 50_000)
+    got, _ = oracle.sort_ex(f, key_type=oracle.KEY_FLOAT32)
+    gf = got.view(np.float32)
+    assert np.array_equal(gf, np.sort(f))                     # -0.0 == +0.0 for NumPy's comparison ...
+    z = np.flatnonzero(gf == 0.0)
+    assert np.all(np.diff(np.signbit(gf[z]).astype(np.int8)) <= 0)  # ... and the total order puts -0 before +0
+    got, _ = oracle.sort_ex(f, key_type=oracle.KEY_FLOAT32, descending=True)
+    assert np.array_equal(got.view(np.float32), np.sort(f)[::-1])
+
+
+def test_sort_ex_nan_total_order(oracle):
+    f = np.array([1.0, np.nan, -1.0, -np.nan, np.inf, -np.inf, 0.0], dtype=np.float32)
+    f[3] = np.float32(np.nan).view(np.uint32).__or__(np.uint32(0x80000000)).view(np.float32)  # negative NaN
+    got, _ = oracle.sort_ex(f, key_type=oracle.KEY_FLOAT32)
+    g = got.view(np.float32)
+    assert np.isnan(g[0]) and np.signbit(g[0]) and np.isnan(g[-1]) and not np.signbit(g[-1])
+    assert np.array_equal(g[1:-1], np.array([-np.inf, -1.0, 0.0, 1.0, np.inf], dtype=np.float32))
+
+
+def test_sort_ex_bit_range_is_a_stable_field_sort(oracle):
+    rng = np.random.default_rng(12)
+    u = rng.integers(0, 1 << 32, 20_000, dtype=np.uint64).astype(np.uint32)
+    v = np.arange(u.size, dtype=np.uint32)
+    for b, e in ((0, 8), (8, 24), (4, 13), (20, 32), (0, 32), (7, 7)):
+        k, p = oracle.sort_ex(u, v, begin_bit=b, end_bit=e)
+        field = (k.astype(np.uint64) >> np.uint64(b)) & np.uint64((1 << (e - b)) - 1)
+        assert np.all(np.diff(field.astype(np.int64)) >= 0)
+        same = np.diff(field.astype(np.int64)) == 0
+        assert np.all(np.diff(p.astype(np.int64))[same] > 0)          # ties keep input order
+        assert np.array_equal(u[p], k)
+    k, p = oracle.sort_ex(u, v, begin_bit=7, end_bit=7)
+    assert np.array_equal(k, u) and np.array_equal(p, v)               # empty range: nothing moves

@@ -34,6 +34,12 @@ VRDX_CUDA_TILE_LOAD_AUTO = 0
 VRDX_CUDA_TILE_LOAD_DIRECT = 1
 VRDX_CUDA_TILE_LOAD_TMA = 2
 
+VRDX_CUDA_KEY_TYPE_UINT32 = 0
+VRDX_CUDA_KEY_TYPE_INT32 = 1
+VRDX_CUDA_KEY_TYPE_FLOAT32 = 2
+VRDX_CUDA_SORT_ORDER_ASCENDING = 0
+VRDX_CUDA_SORT_ORDER_DESCENDING = 1
+
 QUERY_COUNT = 15  # timestamps written per sort (src/vk_radix_sort.h.in:39-50)
 
 
@@ -50,6 +56,12 @@ class VrdxSorterStorageRequirements(Structure):
 class VrdxCudaSorterOptions(Structure):
     _fields_ = [("structSize", c_uint32), ("algorithm", c_int), ("tileLoad", c_int),
                 ("reserved", c_uint32 * 5)]
+
+
+class VrdxCudaSortKeyInfo(Structure):
+    """struct VrdxCudaSortKeyInfo (include/vrdx_cuda.h): key type, order and bit range of vrdxCudaCmdSortEx."""
+    _fields_ = [("structSize", c_uint32), ("keyType", c_int), ("order", c_int), ("beginBit", c_uint32),
+                ("endBit", c_uint32), ("reserved", c_uint32 * 3)]
 
 
 class VrdxCudaSorterProperties(Structure):
@@ -82,6 +94,12 @@ _SIGNATURES = {
     "vrdxCudaImportedMemoryBuffer": (c_void_p, [c_void_p, c_uint64]),
     "vrdxCudaReleaseImportedMemory": (None, [c_void_p]),
     "vrdxCudaGetSorterProperties": (None, [c_void_p, POINTER(VrdxCudaSorterProperties)]),
+    "vrdxCudaCmdSortEx": (None, [c_void_p, c_void_p, POINTER(VrdxCudaSortKeyInfo), c_uint32, c_void_p, c_uint64,
+                                 c_void_p, c_uint64, c_void_p, c_uint64, c_void_p, c_uint64, c_void_p, c_uint32]),
+    "vrdxCudaImportSemaphoreFd": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p)]),
+    "vrdxCudaCmdWaitSemaphore": (c_int, [c_void_p, c_void_p, c_uint64]),
+    "vrdxCudaCmdSignalSemaphore": (c_int, [c_void_p, c_void_p, c_uint64]),
+    "vrdxCudaReleaseImportedSemaphore": (None, [c_void_p]),
     # include/vrdx_dist.h
     "vrdxDistCmdPrefixHistogram": (None, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_uint32, c_uint32, c_uint32,
                                           c_void_p, c_uint64, c_void_p, c_uint64]),
@@ -227,6 +245,23 @@ def vrdxCudaGetQueryPoolResults(pool, first_query: int = 0, query_count: int = Q
     out = (c_uint64 * query_count)()
     res = load_library().vrdxCudaGetQueryPoolResults(pool, first_query, query_count, out)
     return res, list(out)
+
+
+def make_key_info(key_type: int = VRDX_CUDA_KEY_TYPE_UINT32, order: int = VRDX_CUDA_SORT_ORDER_ASCENDING,
+                  begin_bit: int = 0, end_bit: int = 32) -> VrdxCudaSortKeyInfo:
+    info = VrdxCudaSortKeyInfo()
+    info.structSize = ctypes.sizeof(VrdxCudaSortKeyInfo)
+    info.keyType, info.order, info.beginBit, info.endBit = key_type, order, begin_bit, end_bit
+    return info
+
+
+def vrdxCudaCmdSortEx(command_buffer, sorter, key_info, element_count, indirect_buffer, indirect_offset,
+                      keys_buffer, keys_offset, values_buffer, values_offset, storage_buffer, storage_offset,
+                      query_pool=None, query=0) -> None:
+    load_library().vrdxCudaCmdSortEx(command_buffer, sorter, byref(key_info) if key_info is not None else None,
+                                     element_count, indirect_buffer, indirect_offset, keys_buffer, keys_offset,
+                                     values_buffer, values_offset, storage_buffer, storage_offset, query_pool,
+                                     query)
 
 
 def vrdxCudaGetSorterProperties(sorter) -> VrdxCudaSorterProperties:

@@ -45,6 +45,10 @@ struct PassVariant {
   cudaError_t (*launch_downsweep)(cudaStream_t, uint32_t, const PassArgs&);  // reduce-then-scan: scatter pass
   cudaError_t (*launch_upsweep)(cudaStream_t, uint32_t, const PassArgs&);    // reduce-then-scan: tile histograms
   cudaError_t (*launch_inorder)(cudaStream_t, uint32_t, const PassArgs&);    // onesweep, tile id = blockIdx.x (experiment)
+  // the same two kernels compiled for an arbitrary digit plan / key codec (vrdxCudaCmdSortEx); only the
+  // default shapes carry them
+  cudaError_t (*launch_generic)(cudaStream_t, uint32_t, const PassArgs&);
+  cudaError_t (*launch_downsweep_generic)(cudaStream_t, uint32_t, const PassArgs&);
 };
 
 // Launch with (or without) the programmatic-dependent-launch attribute; see GridDepWait().
@@ -81,6 +85,16 @@ cudaError_t PrepareDirect(int* ctas_per_sm) {
                                                        Cfg::kSmemBytes);
 }
 template <class Cfg>
+cudaError_t PrepareDirectWithGeneric(int* ctas_per_sm) {
+  cudaError_t e = cudaFuncSetAttribute(OnesweepKernel<Cfg, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Cfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(OnesweepKernel<Cfg, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)Cfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  return PrepareDirect<Cfg>(ctas_per_sm);
+}
+template <class Cfg>
 cudaError_t PrepareTma(int* ctas_per_sm) {
   cudaError_t e = cudaFuncSetAttribute(OnesweepTmaKernel<Cfg, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)Cfg::kSmemBytes);
@@ -96,6 +110,10 @@ cudaError_t LaunchDirect(cudaStream_t stream, uint32_t grid, const PassArgs& arg
   return LaunchEx(OnesweepKernel<Cfg, MODE>, grid, Cfg::kThreads, Cfg::kSmemBytes, stream, true, args);
 }
 template <class Cfg, int MODE>
+cudaError_t LaunchDirectGeneric(cudaStream_t stream, uint32_t grid, const PassArgs& args) {
+  return LaunchEx(OnesweepKernel<Cfg, MODE, true>, grid, Cfg::kThreads, Cfg::kSmemBytes, stream, true, args);
+}
+template <class Cfg, int MODE>
 cudaError_t LaunchTma(cudaStream_t stream, uint32_t grid, const PassArgs& args) {
   return LaunchEx(OnesweepTmaKernel<Cfg, MODE>, grid, Cfg::kThreads, Cfg::kSmemBytes, stream, true, args);
 }
@@ -103,13 +121,23 @@ template <class Cfg>
 cudaError_t LaunchUpsweep(cudaStream_t stream, uint32_t grid, const PassArgs& args) {
   // the first kernel of a sort (pass 0) is a normal launch: it must wait for the caller's prior work
   return LaunchEx(UpsweepKernel<Cfg::kTile>, grid, kUpsweepThreads, 0, stream, args.pass != 0, args.indirect,
-                  args.n_or_max, args.pass, args.keys_in, args.status, args.status_next, args.hdr, args.ts_end);
+                  args.n_or_max, args.shift, args.mask, args.codec_in, args.keys_in, args.status, args.status_next,
+                  args.hdr, args.ts_end);
 }
 template <int T, int I, bool KV, int M, int LB = 4, bool PAIRED = false>
 constexpr PassVariant MakeVariant() {
   using Cfg = PassConfig<T, I, KV, M, LB, PAIRED>;
   return PassVariant{T, I, M, false, 0, (uint32_t)Cfg::kTile, Cfg::kSmemBytes, &PrepareDirect<Cfg>,
-                     &LaunchDirect<Cfg, 0>, &LaunchDirect<Cfg, 1>, &LaunchUpsweep<Cfg>, &LaunchDirect<Cfg, 2>};
+                     &LaunchDirect<Cfg, 0>, &LaunchDirect<Cfg, 1>, &LaunchUpsweep<Cfg>, &LaunchDirect<Cfg, 2>,
+                     nullptr, nullptr};
+}
+// A default shape: also compiled for arbitrary digit plans and key codecs.
+template <int T, int I, bool KV, int M>
+constexpr PassVariant MakeDefaultVariant() {
+  using Cfg = PassConfig<T, I, KV, M, 4, false>;
+  return PassVariant{T, I, M, false, 0, (uint32_t)Cfg::kTile, Cfg::kSmemBytes, &PrepareDirectWithGeneric<Cfg>,
+                     &LaunchDirect<Cfg, 0>, &LaunchDirect<Cfg, 1>, &LaunchUpsweep<Cfg>, &LaunchDirect<Cfg, 2>,
+                     &LaunchDirectGeneric<Cfg, 0>, &LaunchDirectGeneric<Cfg, 1>};
 }
 template <class Cfg, int C>
 cudaError_t PrepareCluster(int* ctas_per_sm) {
@@ -143,13 +171,13 @@ template <int T, int I, bool KV, int M, int C, int LB = 4>
 constexpr PassVariant MakeClusterVariant() {
   using Cfg = PassConfig<T, I, KV, M, LB>;
   return PassVariant{T, I, M, false, C, (uint32_t)Cfg::kTile, Cfg::kSmemBytes, &PrepareCluster<Cfg, C>,
-                     &LaunchCluster<Cfg, C>, &LaunchDirect<Cfg, 1>, &LaunchUpsweep<Cfg>, nullptr};
+                     &LaunchCluster<Cfg, C>, &LaunchDirect<Cfg, 1>, &LaunchUpsweep<Cfg>, nullptr, nullptr, nullptr};
 }
 template <int T, int I, bool KV, int M, int LB = 4>
 constexpr PassVariant MakeTmaVariant() {
   using Cfg = TmaPassConfig<T, I, KV, M, LB>;
   return PassVariant{T, I, M, true, 0, (uint32_t)Cfg::kTile, Cfg::kSmemBytes, &PrepareTma<Cfg>, &LaunchTma<Cfg, 0>,
-                     &LaunchTma<Cfg, 1>, &LaunchUpsweep<Cfg>, nullptr};
+                     &LaunchTma<Cfg, 1>, &LaunchUpsweep<Cfg>, nullptr, nullptr, nullptr};
 }
 
 // Direct-load variants (one tile per CTA).  Defaults (measured on B200, profiles/):
@@ -159,14 +187,14 @@ constexpr PassVariant MakeTmaVariant() {
 // The rest are kept selectable for A/B runs (VrdxCudaSorterOptions::reserved / VRDX_*_VARIANT) and
 // are exercised by the test-suite where they change the algorithm (cluster look-back, paired staging).
 static const PassVariant kKeysVariants[] = {
-    MakeVariant<384, 16, false, 3>(),           MakeVariant<256, 16, false, 5>(),
+    MakeDefaultVariant<384, 16, false, 3>(),    MakeDefaultVariant<256, 16, false, 5>(),
     MakeVariant<512, 16, false, 2>(),           MakeVariant<256, 16, false, 4>(),
     MakeVariant<384, 12, false, 4>(),           MakeClusterVariant<384, 16, false, 3, 4>(),
     MakeClusterVariant<384, 16, false, 3, 8>(), MakeVariant<384, 16, false, 3, 16>(),
     MakeVariant<384, 16, false, 3>(),  // placeholder so keys and pairs tables index alike
 };
 static const PassVariant kPairVariants[] = {
-    MakeVariant<384, 16, true, 3>(),            MakeVariant<256, 16, true, 5>(),
+    MakeDefaultVariant<384, 16, true, 3>(),     MakeVariant<256, 16, true, 5>(),
     MakeVariant<512, 16, true, 2>(),            MakeVariant<256, 16, true, 4>(),
     MakeVariant<384, 12, true, 4>(),            MakeClusterVariant<384, 16, true, 3, 4>(),
     MakeClusterVariant<384, 16, true, 3, 8>(),  MakeVariant<384, 16, true, 3, 16>(),
@@ -174,6 +202,7 @@ static const PassVariant kPairVariants[] = {
 };
 constexpr int kDefaultKeysRtsVariant = 1;
 constexpr int kDefaultPairRtsVariant = 0;
+constexpr int kDefaultOnesweepVariant = 0;  // keys and pairs
 // Persistent TMA-staged variants (selected only with VRDX_CUDA_TILE_LOAD_TMA; measured slower than
 // the direct kernels on B200).
 static const PassVariant kKeysTmaVariants[] = {
@@ -227,6 +256,12 @@ struct VrdxCudaImportedMemory_T {
   uint64_t size = 0;
 };
 
+struct VrdxCudaImportedSemaphore_T {
+  int device = 0;
+  cudaExternalSemaphore_t ext = nullptr;
+  bool timeline = false;
+};
+
 namespace {
 
 int DeviceFromHandle(const void* h) { return (int)(reinterpret_cast<uintptr_t>(h)) - 1; }
@@ -273,12 +308,56 @@ struct Stamps {
   }
 };
 
+// What a sort compares: the reference's plan (uint32 ascending, four 8-bit digits) or the plan
+// of a VrdxCudaSortKeyInfo (key type / order as a codec, bit sub-range as fewer, narrower digits).
+struct SortPlan {
+  DigitPlan digits;
+  bool reference;   // exactly the reference's sort: every kernel flavour implements it
+  bool all_bits;    // the digits cover all 32 bits: equal keys are indistinguishable
+};
+
+SortPlan ReferencePlan() {
+  SortPlan p{};
+  p.digits.passes = kPasses;
+  for (int i = 0; i < kPasses; ++i) {
+    p.digits.shift[i] = (uint32_t)(i * kRadixBits);
+    p.digits.mask[i] = kRadix - 1;
+  }
+  p.reference = true;
+  p.all_bits = true;
+  return p;
+}
+
+bool PlanFromKeyInfo(const VrdxCudaSortKeyInfo* info, SortPlan* out) {
+  *out = ReferencePlan();
+  if (!info) return true;
+  if (info->structSize < sizeof(VrdxCudaSortKeyInfo) || info->beginBit > info->endBit || info->endBit > 32 ||
+      (uint32_t)info->keyType > (uint32_t)VRDX_CUDA_KEY_TYPE_FLOAT32 ||
+      (uint32_t)info->order > (uint32_t)VRDX_CUDA_SORT_ORDER_DESCENDING)
+    return false;
+  DigitPlan& d = out->digits;
+  const uint32_t bits = info->endBit - info->beginBit;
+  d.passes = (bits + kRadixBits - 1) / kRadixBits;
+  for (uint32_t i = 0; i < (uint32_t)kPasses; ++i) {
+    const uint32_t lo = info->beginBit + i * kRadixBits;
+    const uint32_t width = i < d.passes ? (info->endBit - lo < (uint32_t)kRadixBits ? info->endBit - lo : kRadixBits) : 0;
+    d.shift[i] = i < d.passes ? lo : 0;
+    d.mask[i] = (1u << width) - 1u;
+  }
+  d.codec.cmask = info->keyType == VRDX_CUDA_KEY_TYPE_UINT32 ? 0u : 0x80000000u;
+  d.codec.fmask = info->keyType == VRDX_CUDA_KEY_TYPE_FLOAT32 ? 0x7FFFFFFFu : 0u;
+  d.codec.dmask = info->order == VRDX_CUDA_SORT_ORDER_DESCENDING ? 0xFFFFFFFFu : 0u;
+  out->all_bits = bits == 32;
+  out->reference = out->all_bits && !d.codec.cmask && !d.codec.fmask && !d.codec.dmask;
+  return true;
+}
+
 // The body of every vrdxCmdSort* (reference: gpuSort, h.in:344-507).
 void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or_max,
                  VkBuffer indirectBuffer, VkDeviceSize indirectOffset, VkBuffer keysBuffer,
                  VkDeviceSize keysOffset, VkBuffer valuesBuffer, VkDeviceSize valuesOffset,
                  VkBuffer storageBuffer, VkDeviceSize storageOffset, VkQueryPool queryPool,
-                 uint32_t query) {
+                 uint32_t query, const SortPlan& plan = ReferencePlan()) {
   if (!sorter) return;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(commandBuffer);
   DeviceGuard guard(sorter->device);
@@ -305,8 +384,9 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
       NoteError(sorter, cudaGetLastError());
     }
   }
-  if (n_or_max == 0 || !keys || !storage) {
-    if (n_or_max != 0) NoteError(sorter, cudaErrorInvalidValue);
+  const uint32_t passes = plan.digits.passes;
+  if (n_or_max == 0 || !keys || !storage || passes == 0) {
+    if (n_or_max != 0 && passes != 0) NoteError(sorter, cudaErrorInvalidValue);
     for (int i = 1; i < 15; ++i) st.Same(i);
     sorter->last_launches.store(0);
     return;
@@ -327,11 +407,17 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
   // TMA staging needs 16-byte aligned sources in both ping-pong directions.
   auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   const bool can_tma = aligned16(keys) && aligned16(storage) && (!kv || aligned16(values));
-  const bool use_tma = sorter->tile_load == VRDX_CUDA_TILE_LOAD_TMA && can_tma;
+  // Key types, order and bit sub-ranges are implemented by the direct-load tile kernel; the
+  // experimental flavours (persistent TMA staging, cluster look-back) only know the reference's plan.
+  // Only the default shapes are compiled for them, so such a sort ignores the sorter's A/B selectors.
+  const bool generic = !plan.reference;
+  const bool use_tma = sorter->tile_load == VRDX_CUDA_TILE_LOAD_TMA && can_tma && !generic;
   const PassVariant& variant =
-      use_tma ? (kv ? kPairTmaVariants[sorter->pair_tma_variant] : kKeysTmaVariants[sorter->keys_tma_variant])
-              : use_rts ? (kv ? kPairVariants[sorter->pair_rts_variant] : kKeysVariants[sorter->keys_rts_variant])
-                        : (kv ? kPairVariants[sorter->pair_variant] : kKeysVariants[sorter->keys_variant]);
+      generic ? (use_rts ? (kv ? kPairVariants[kDefaultPairRtsVariant] : kKeysVariants[kDefaultKeysRtsVariant])
+                         : (kv ? kPairVariants[kDefaultOnesweepVariant] : kKeysVariants[kDefaultOnesweepVariant]))
+      : use_tma ? (kv ? kPairTmaVariants[sorter->pair_tma_variant] : kKeysTmaVariants[sorter->keys_tma_variant])
+      : use_rts ? (kv ? kPairVariants[sorter->pair_rts_variant] : kKeysVariants[sorter->keys_rts_variant])
+                : (kv ? kPairVariants[sorter->pair_variant] : kKeysVariants[sorter->keys_variant]);
   const uint32_t tiles = (uint32_t)CeilDiv(n_or_max, variant.tile);
   uint32_t pass_grid = tiles;
   if (!use_rts && !use_tma && variant.cluster > 1)  // whole clusters; CTAs past the count only serve their digit slice
@@ -352,28 +438,34 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
       // lane-private (conflict-free) bins, one 1024-thread CTA per SM
       uint64_t chunks = CeilDiv(n_or_max, (uint64_t)kHistPrivChunk);
       uint32_t grid = (uint32_t)(chunks < (uint64_t)sorter->sm_count ? chunks : (uint64_t)sorter->sm_count);
-      NoteError(sorter, LaunchEx(HistogramKernelPrivate, grid, kHistPrivThreads, kHistPrivSmemBytes, stream, false,
-                                 (const uint32_t*)keys, indirect, n_or_max, hdr, st.Written(1)));
+      NoteError(sorter, LaunchEx(generic ? HistogramKernelPrivate<true> : HistogramKernelPrivate<false>, grid,
+                                 kHistPrivThreads, kHistPrivSmemBytes, stream, false, (const uint32_t*)keys, indirect,
+                                 n_or_max, hdr, st.Written(1), plan.digits));
     } else {
       uint64_t chunks = CeilDiv(n_or_max, (uint64_t)kHistChunk);
       uint64_t cap = (uint64_t)sorter->sm_count * 4;
       uint32_t grid = (uint32_t)(chunks < cap ? (chunks ? chunks : 1) : cap);
-      NoteError(sorter, LaunchEx(HistogramKernel, grid, kHistThreads, 0, stream, false, (const uint32_t*)keys, indirect,
-                                 n_or_max, hdr, st.Written(1)));
+      NoteError(sorter, LaunchEx(generic ? HistogramKernel<true> : HistogramKernel<false>, grid, kHistThreads, 0, stream,
+                                 false, (const uint32_t*)keys, indirect, n_or_max, hdr, st.Written(1), plan.digits));
     }
     ++launches;
   } else {
     st.Same(1);  // reduce-then-scan keeps no state across passes: every table it reads is written first
   }
 
-  for (uint32_t pass = 0; pass < (uint32_t)kPasses; ++pass) {
+  for (uint32_t pass = 0; pass < passes; ++pass) {
     PassArgs args{};
     args.indirect = indirect;
     args.n_or_max = n_or_max;
     args.pass = pass;
+    args.shift = plan.digits.shift[pass];
+    args.mask = plan.digits.mask[pass];
+    if (pass == 0) args.codec_in = plan.digits.codec;
+    if (pass + 1 == passes) args.codec_out = plan.digits.codec;
+    args.order_free = (!kv && pass == 0 && plan.all_bits) ? 1u : 0u;
     args.hdr = hdr;
     args.status = status[pass & 1];
-    args.status_next = (pass + 1 < (uint32_t)kPasses) ? status[(pass + 1) & 1] : nullptr;
+    args.status_next = (pass + 1 < passes) ? status[(pass + 1) & 1] : nullptr;
     // ping-pong: user -> scratch on even passes, scratch -> user on odd ones (h.in:417-427)
     args.keys_in = (pass & 1) ? keys_alt : keys;
     args.keys_out = (pass & 1) ? keys : keys_alt;
@@ -397,7 +489,8 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
                                  n_or_max, variant.tile, status[1], (const uint32_t*)seg,
                                  st.Written(2 + 3 * pass + 1)));
       args.ts_end = st.Written(2 + 3 * pass + 2);
-      NoteError(sorter, variant.launch_downsweep(stream, use_tma ? pass_grid : tiles, args));
+      NoteError(sorter, generic ? variant.launch_downsweep_generic(stream, tiles, args)
+                                : variant.launch_downsweep(stream, use_tma ? pass_grid : tiles, args));
       launches += 4;
       continue;
     }
@@ -406,11 +499,24 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
     st.Same(2 + 3 * pass + 1);
     args.ts_end = st.Written(2 + 3 * pass + 2);
     static const bool inorder = getenv("VRDX_TILE_ORDER") && atoi(getenv("VRDX_TILE_ORDER")) == 1;
-    NoteError(sorter, (inorder && variant.launch_inorder) ? variant.launch_inorder(stream, pass_grid, args)
-                                                          : variant.launch(stream, pass_grid, args));
+    NoteError(sorter, generic                               ? variant.launch_generic(stream, pass_grid, args)
+                      : (inorder && variant.launch_inorder) ? variant.launch_inorder(stream, pass_grid, args)
+                                                            : variant.launch(stream, pass_grid, args));
     ++launches;
   }
-  st.Same(14);
+  for (uint32_t pass = passes; pass < (uint32_t)kPasses; ++pass)  // passes a bit sub-range does not need
+    for (int j = 0; j < 3; ++j) st.Same(2 + 3 * (int)pass + j);
+  if (passes & 1u) {
+    // an odd number of passes ends in the scratch halves: bring [0, count) home
+    const uint64_t blocks = CeilDiv((uint64_t)n_or_max, (uint64_t)1024);
+    const uint64_t cap = (uint64_t)sorter->sm_count * 8;
+    NoteError(sorter, LaunchEx(CopyBackKernel, (uint32_t)(blocks < cap ? blocks : cap), 256u, 0, stream, true, indirect,
+                               n_or_max, (const uint32_t*)keys_alt, keys, kv ? (const uint32_t*)vals_alt : nullptr,
+                               kv ? values : nullptr, st.Written(14)));
+    ++launches;
+  } else {
+    st.Same(14);
+  }
   sorter->last_launches.store(launches);
 }
 
@@ -467,7 +573,11 @@ VkResult vrdxCudaCreateSorter(const VrdxSorterCreateInfo* pCreateInfo,
   // CTAs of each are co-resident per SM (the persistent kernels launch exactly one such wave).
   int keys_ctas = 1, pair_ctas = 1, keys_tma_ctas = 1, pair_tma_ctas = 1;
   int unused = 0;
-  if (kKeysVariants[keys_rts_variant].prepare(&unused) != cudaSuccess ||
+  if (kKeysVariants[kDefaultOnesweepVariant].prepare(&unused) != cudaSuccess ||  // vrdxCudaCmdSortEx runs the defaults
+      kPairVariants[kDefaultOnesweepVariant].prepare(&unused) != cudaSuccess ||
+      kKeysVariants[kDefaultKeysRtsVariant].prepare(&unused) != cudaSuccess ||
+      kPairVariants[kDefaultPairRtsVariant].prepare(&unused) != cudaSuccess ||
+      kKeysVariants[keys_rts_variant].prepare(&unused) != cudaSuccess ||
       kPairVariants[pair_rts_variant].prepare(&unused) != cudaSuccess ||
       kKeysVariants[keys_variant].prepare(&keys_ctas) != cudaSuccess ||
       kPairVariants[pair_variant].prepare(&pair_ctas) != cudaSuccess ||
@@ -497,7 +607,9 @@ VkResult vrdxCudaCreateSorter(const VrdxSorterCreateInfo* pCreateInfo,
   if (const char* e = getenv("VRDX_ALGORITHM")) s->algorithm = (VrdxCudaAlgorithm)atoi(e);
   if (const char* e = getenv("VRDX_PDL")) g_pdl = atoi(e) != 0;
   if (const char* e = getenv("VRDX_HIST_PRIVATE_MIN")) g_hist_private_min_count = (uint32_t)strtoul(e, nullptr, 10);
-  if (cudaFuncSetAttribute(HistogramKernelPrivate, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if (cudaFuncSetAttribute(HistogramKernelPrivate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)kHistPrivSmemBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(HistogramKernelPrivate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)kHistPrivSmemBytes) != cudaSuccess) {
     cudaGetLastError();
     delete s;
@@ -581,6 +693,21 @@ void vrdxCmdSortKeyValueIndirect(VkCommandBuffer commandBuffer, VrdxSorter sorte
 }
 
 // ---------------------------------------------------------------------------- extensions
+
+void vrdxCudaCmdSortEx(VkCommandBuffer commandBuffer, VrdxSorter sorter, const VrdxCudaSortKeyInfo* pKeyInfo,
+                       uint32_t elementCount, VkBuffer indirectBuffer, VkDeviceSize indirectOffset,
+                       VkBuffer keysBuffer, VkDeviceSize keysOffset, VkBuffer valuesBuffer,
+                       VkDeviceSize valuesOffset, VkBuffer storageBuffer, VkDeviceSize storageOffset,
+                       VkQueryPool queryPool, uint32_t query) {
+  if (!sorter) return;
+  SortPlan plan;
+  if (!PlanFromKeyInfo(pKeyInfo, &plan)) {
+    NoteError(sorter, cudaErrorInvalidValue);
+    return;
+  }
+  EnqueueSort(commandBuffer, sorter, elementCount, indirectBuffer, indirectOffset, keysBuffer, keysOffset,
+              valuesBuffer, valuesOffset, storageBuffer, storageOffset, queryPool, query, plan);
+}
 
 int vrdxCudaGetLastError(VrdxSorter sorter) {
   if (!sorter) return (int)cudaErrorInvalidResourceHandle;
@@ -707,6 +834,69 @@ void vrdxCudaReleaseImportedMemory(VrdxCudaImportedMemory memory) {
   cudaFree(memory->base);
   cudaDestroyExternalMemory(memory->ext);
   delete memory;
+}
+
+VkResult vrdxCudaImportSemaphoreFd(VkDevice device, int fd, int timeline, VrdxCudaImportedSemaphore* pSemaphore) {
+  if (!pSemaphore || fd < 0) return VK_ERROR_INITIALIZATION_FAILED;
+  const int dev = DeviceFromHandle(device);
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || dev < 0 || dev >= count) {
+    cudaGetLastError();
+    return VK_ERROR_INITIALIZATION_FAILED;
+  }
+  DeviceGuard guard(dev);
+  cudaExternalSemaphoreHandleDesc hd{};
+  hd.type = timeline ? cudaExternalSemaphoreHandleTypeTimelineSemaphoreFd : cudaExternalSemaphoreHandleTypeOpaqueFd;
+  hd.handle.fd = fd;
+  cudaExternalSemaphore_t ext = nullptr;
+  if (cudaImportExternalSemaphore(&ext, &hd) != cudaSuccess) {
+    cudaGetLastError();
+    return VK_ERROR_INITIALIZATION_FAILED;
+  }
+  VrdxCudaImportedSemaphore_T* s = new (std::nothrow) VrdxCudaImportedSemaphore_T();
+  if (!s) {
+    cudaDestroyExternalSemaphore(ext);
+    return VK_ERROR_OUT_OF_HOST_MEMORY;
+  }
+  s->device = dev;
+  s->ext = ext;
+  s->timeline = timeline != 0;
+  *pSemaphore = s;
+  return VK_SUCCESS;
+}
+
+VkResult vrdxCudaCmdWaitSemaphore(VkCommandBuffer commandBuffer, VrdxCudaImportedSemaphore semaphore, uint64_t value) {
+  if (!semaphore) return VK_ERROR_INITIALIZATION_FAILED;
+  DeviceGuard guard(semaphore->device);
+  cudaExternalSemaphoreWaitParams wp{};
+  wp.params.fence.value = semaphore->timeline ? value : 0;
+  if (cudaWaitExternalSemaphoresAsync(&semaphore->ext, &wp, 1, reinterpret_cast<cudaStream_t>(commandBuffer)) !=
+      cudaSuccess) {
+    cudaGetLastError();
+    return VK_ERROR_UNKNOWN;
+  }
+  return VK_SUCCESS;
+}
+
+VkResult vrdxCudaCmdSignalSemaphore(VkCommandBuffer commandBuffer, VrdxCudaImportedSemaphore semaphore,
+                                    uint64_t value) {
+  if (!semaphore) return VK_ERROR_INITIALIZATION_FAILED;
+  DeviceGuard guard(semaphore->device);
+  cudaExternalSemaphoreSignalParams sp{};
+  sp.params.fence.value = semaphore->timeline ? value : 0;
+  if (cudaSignalExternalSemaphoresAsync(&semaphore->ext, &sp, 1, reinterpret_cast<cudaStream_t>(commandBuffer)) !=
+      cudaSuccess) {
+    cudaGetLastError();
+    return VK_ERROR_UNKNOWN;
+  }
+  return VK_SUCCESS;
+}
+
+void vrdxCudaReleaseImportedSemaphore(VrdxCudaImportedSemaphore semaphore) {
+  if (!semaphore) return;
+  DeviceGuard guard(semaphore->device);
+  cudaDestroyExternalSemaphore(semaphore->ext);
+  delete semaphore;
 }
 
 void vrdxCudaGetSorterProperties(VrdxSorter sorter, VrdxCudaSorterProperties* p) {

@@ -82,6 +82,34 @@ __device__ __forceinline__ uint32_t ResolveCount(const uint32_t* indirect, uint3
   return c < n_or_max ? c : n_or_max;
 }
 
+// Key codec (extension, absent from the reference: include/vrdx_cuda.h VrdxCudaSortKeyInfo).
+// The passes always sort plain unsigned 32-bit words.  Other key types and descending order are
+// order-preserving bijections onto such words, applied where the FIRST pass reads the caller's
+// keys (KeyIn) and undone where the LAST pass stores them (KeyOut), so they cost no extra pass:
+//   int32    flip the sign bit                        cmask = 0x80000000
+//   float32  negative: flip all bits, else sign bit   cmask = 0x80000000, fmask = 0x7FFFFFFF
+//   descending: complement the word                   dmask = 0xFFFFFFFF
+// All-zero masks are the identity (the reference's uint32 ascending sort).
+struct KeyCodec {
+  uint32_t fmask, cmask, dmask;
+};
+__device__ __forceinline__ uint32_t KeyIn(uint32_t k, const KeyCodec c) {
+  return k ^ ((uint32_t)((int32_t)k >> 31) & c.fmask) ^ (c.cmask ^ c.dmask);
+}
+__device__ __forceinline__ uint32_t KeyOut(uint32_t t, const KeyCodec c) {
+  const uint32_t u = t ^ c.dmask;
+  return u ^ ((uint32_t)(~(int32_t)u >> 31) & c.fmask) ^ c.cmask;
+}
+// Digit plan of one sort: pass p ranks by (word >> shift[p]) & mask[p].  The reference is
+// passes = 4, shift = 0/8/16/24, mask = 0xFF; a bit sub-range [begin, end) uses fewer passes and a
+// narrower last digit.
+struct DigitPlan {
+  uint32_t passes;
+  uint32_t shift[kPasses];
+  uint32_t mask[kPasses];
+  KeyCodec codec;  // applied by whoever reads the caller's keys
+};
+
 // ------------------------------------------------------------------------------------------
 // HistogramKernel — all four digit histograms in one pass over the keys + exclusive scan.
 // Algorithmic traffic: 4 B/key read.  Grid: a multiple of the SM count (persistent, grid-stride
@@ -91,16 +119,28 @@ constexpr int kHistThreads = 512;
 constexpr int kHistVecPerThread = 4;                                   // uint4 loads per thread per chunk
 constexpr int kHistChunk = kHistThreads * kHistVecPerThread * 4;       // keys per chunk
 
-__device__ __forceinline__ void HistCount(uint32_t (*sh)[kRadix], uint32_t k) {
-  atomicAdd(&sh[0][k & 0xFFu], 1u);
-  atomicAdd(&sh[1][(k >> 8) & 0xFFu], 1u);
-  atomicAdd(&sh[2][(k >> 16) & 0xFFu], 1u);
-  atomicAdd(&sh[3][k >> 24], 1u);
+// GENERIC = false is the reference's plan with everything folded at compile time (the hot default);
+// GENERIC = true reads the plan of a VrdxCudaSortKeyInfo.
+template <bool GENERIC>
+__device__ __forceinline__ void HistCount(uint32_t (*sh)[kRadix], uint32_t raw, const DigitPlan& plan) {
+  if (!GENERIC) {
+    atomicAdd(&sh[0][raw & 0xFFu], 1u);
+    atomicAdd(&sh[1][(raw >> 8) & 0xFFu], 1u);
+    atomicAdd(&sh[2][(raw >> 16) & 0xFFu], 1u);
+    atomicAdd(&sh[3][raw >> 24], 1u);
+  } else {
+    const uint32_t k = KeyIn(raw, plan.codec);
+#pragma unroll
+    for (int p = 0; p < kPasses; ++p)
+      if ((uint32_t)p < plan.passes) atomicAdd(&sh[p][(k >> plan.shift[p]) & plan.mask[p]], 1u);
+  }
 }
 
+template <bool GENERIC>
 __global__ void __launch_bounds__(kHistThreads)
 HistogramKernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ indirect,
-                uint32_t n_or_max, StorageHeader* __restrict__ hdr, unsigned long long* ts_end) {
+                uint32_t n_or_max, StorageHeader* __restrict__ hdr, unsigned long long* ts_end,
+                const DigitPlan plan) {
   __shared__ uint32_t sh[kPasses][kRadix];
   __shared__ uint32_t s_last;
   const int tid = threadIdx.x;
@@ -128,7 +168,8 @@ HistogramKernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ 
       for (int j = 0; j < kHistVecPerThread; ++j) v[j] = __ldcs(body + base + j * kHistThreads + tid);
 #pragma unroll
       for (int j = 0; j < kHistVecPerThread; ++j) {
-        HistCount(sh, v[j].x); HistCount(sh, v[j].y); HistCount(sh, v[j].z); HistCount(sh, v[j].w);
+        HistCount<GENERIC>(sh, v[j].x, plan); HistCount<GENERIC>(sh, v[j].y, plan);
+        HistCount<GENERIC>(sh, v[j].z, plan); HistCount<GENERIC>(sh, v[j].w, plan);
       }
     } else {
 #pragma unroll
@@ -136,15 +177,16 @@ HistogramKernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ 
         uint64_t idx = base + (uint64_t)j * kHistThreads + tid;
         if (idx < nvec) {
           uint4 q = __ldcs(body + idx);
-          HistCount(sh, q.x); HistCount(sh, q.y); HistCount(sh, q.z); HistCount(sh, q.w);
+          HistCount<GENERIC>(sh, q.x, plan); HistCount<GENERIC>(sh, q.y, plan);
+          HistCount<GENERIC>(sh, q.z, plan); HistCount<GENERIC>(sh, q.w, plan);
         }
       }
     }
   }
   if (blockIdx.x == 0) {  // unaligned head (< 4 keys) and the n % 4 tail
-    if ((uint32_t)tid < head) HistCount(sh, keys[tid]);
+    if ((uint32_t)tid < head) HistCount<GENERIC>(sh, keys[tid], plan);
     const uint32_t t = tail_start + tid;
-    if (tid < 4 && t < n) HistCount(sh, keys[t]);
+    if (tid < 4 && t < n) HistCount<GENERIC>(sh, keys[t], plan);
   }
   __syncthreads();
 
@@ -188,16 +230,27 @@ constexpr int kHistPrivThreads = 1024;
 constexpr int kHistPrivChunk = kHistPrivThreads * kHistVecPerThread * 4;  // keys per CTA per iteration
 constexpr size_t kHistPrivSmemBytes = (size_t)kPasses * kRadix * 32 * sizeof(uint32_t);
 
-__device__ __forceinline__ void HistCountPrivate(uint32_t* sh, uint32_t lane, uint32_t k) {
-  atomicAdd(&sh[((0 * kRadix + (k & 0xFFu)) << 5) + lane], 1u);
-  atomicAdd(&sh[((1 * kRadix + ((k >> 8) & 0xFFu)) << 5) + lane], 1u);
-  atomicAdd(&sh[((2 * kRadix + ((k >> 16) & 0xFFu)) << 5) + lane], 1u);
-  atomicAdd(&sh[((3 * kRadix + (k >> 24)) << 5) + lane], 1u);
+template <bool GENERIC>
+__device__ __forceinline__ void HistCountPrivate(uint32_t* sh, uint32_t lane, uint32_t raw, const DigitPlan& plan) {
+  if (!GENERIC) {
+    atomicAdd(&sh[((0 * kRadix + (raw & 0xFFu)) << 5) + lane], 1u);
+    atomicAdd(&sh[((1 * kRadix + ((raw >> 8) & 0xFFu)) << 5) + lane], 1u);
+    atomicAdd(&sh[((2 * kRadix + ((raw >> 16) & 0xFFu)) << 5) + lane], 1u);
+    atomicAdd(&sh[((3 * kRadix + (raw >> 24)) << 5) + lane], 1u);
+  } else {
+    const uint32_t k = KeyIn(raw, plan.codec);
+#pragma unroll
+    for (int p = 0; p < kPasses; ++p)
+      if ((uint32_t)p < plan.passes)
+        atomicAdd(&sh[((p * kRadix + ((k >> plan.shift[p]) & plan.mask[p])) << 5) + lane], 1u);
+  }
 }
 
+template <bool GENERIC>
 __global__ void __launch_bounds__(kHistPrivThreads, 1)
 HistogramKernelPrivate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ indirect,
-                       uint32_t n_or_max, StorageHeader* __restrict__ hdr, unsigned long long* ts_end) {
+                       uint32_t n_or_max, StorageHeader* __restrict__ hdr, unsigned long long* ts_end,
+                       const DigitPlan plan) {
   extern __shared__ __align__(16) uint32_t sh[];  // [4][256][32]
   __shared__ uint32_t s_last;
   const int tid = threadIdx.x;
@@ -230,15 +283,15 @@ HistogramKernelPrivate(const uint32_t* __restrict__ keys, const uint32_t* __rest
 #pragma unroll
     for (int j = 0; j < kHistVecPerThread; ++j) {
       if (base + (uint64_t)j * kHistPrivThreads + tid < nvec) {
-        HistCountPrivate(sh, lane, v[j].x); HistCountPrivate(sh, lane, v[j].y);
-        HistCountPrivate(sh, lane, v[j].z); HistCountPrivate(sh, lane, v[j].w);
+        HistCountPrivate<GENERIC>(sh, lane, v[j].x, plan); HistCountPrivate<GENERIC>(sh, lane, v[j].y, plan);
+        HistCountPrivate<GENERIC>(sh, lane, v[j].z, plan); HistCountPrivate<GENERIC>(sh, lane, v[j].w, plan);
       }
     }
   }
   if (blockIdx.x == 0) {  // unaligned head (< 4 keys) and the n % 4 tail
-    if ((uint32_t)tid < head) HistCountPrivate(sh, lane, keys[tid]);
+    if ((uint32_t)tid < head) HistCountPrivate<GENERIC>(sh, lane, keys[tid], plan);
     const uint32_t t = tail_start + tid;
-    if (tid < 4 && t < n) HistCountPrivate(sh, lane, keys[t]);
+    if (tid < 4 && t < n) HistCountPrivate<GENERIC>(sh, lane, keys[t], plan);
   }
   __syncthreads();
 
@@ -307,6 +360,11 @@ struct PassArgs {
   const uint32_t* vals_in;
   uint32_t* vals_out;
   unsigned long long* ts_end;  // query-pool slot stamped when this kernel finishes (or nullptr)
+  // digit of this pass: (word >> shift) & mask (the reference: shift = 8 * pass, mask = 0xFF)
+  uint32_t shift, mask;
+  KeyCodec codec_in;    // non-zero only on the first pass: caller's key type/order -> sortable word
+  KeyCodec codec_out;   // non-zero only on the last pass: sortable word -> caller's key type/order
+  uint32_t order_free;  // 1: keys-only first pass of a sort over all 32 bits (no order to preserve)
 };
 
 constexpr int kSpineChunk = 8;         // reduce-then-scan: tiles per upsweep CTA / spine chunk
@@ -439,7 +497,9 @@ __device__ __forceinline__ uint32_t LookBack(const uint32_t* status, uint32_t ti
 // MODE 1: downsweep of the reduce-then-scan variant — tile id = blockIdx.x and `a.status` already
 //         holds the exclusive prefix over tiles of every digit (UpsweepKernel + Spine*Kernel), so
 //         the kernel has no inter-CTA communication at all (the reference's downsweep shape).
-template <class Cfg, int MODE = 0>
+// GENERIC = false: the reference's plan (shift = 8 * pass, mask = 0xFF, no codec) folded at compile
+// time — the code the measurements in DESIGN.md are about.  GENERIC = true: digit and codec from PassArgs.
+template <class Cfg, int MODE = 0, bool GENERIC = false>
 __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinCtas)
 OnesweepKernel(const PassArgs a) {
   constexpr int THREADS = Cfg::kThreads;
@@ -459,7 +519,10 @@ OnesweepKernel(const PassArgs a) {
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const uint32_t shift = a.pass * kRadixBits;
+  const uint32_t shift = GENERIC ? a.shift : a.pass * kRadixBits;
+  const uint32_t mask = GENERIC ? a.mask : (uint32_t)(kRadix - 1);
+  const KeyCodec cin = GENERIC ? a.codec_in : KeyCodec{0u, 0u, 0u};    // identity codecs fold away
+  const KeyCodec cout = GENERIC ? a.codec_out : KeyCodec{0u, 0u, 0u};
   const uint32_t n = ResolveCount(a.indirect, a.n_or_max);
   GridDepLaunch();
   {
@@ -472,7 +535,8 @@ OnesweepKernel(const PassArgs a) {
   // the look-back is already resident (forward progress without relying on blockIdx order).
   // Keys-only onesweep pass 0 is order-free (see the ranking below): tiles claim their output
   // ranges with global atomics, so it needs neither tickets nor the look-back chain.
-  const bool unordered = (MODE != 1) && !KV && a.pass == 0;
+  const bool order_free = !KV && a.order_free != 0u;
+  const bool unordered = (MODE != 1) && order_free;
   if (MODE == 0 && !unordered && tid == 0) s_misc[8] = atomicAdd(&a.hdr->tickets[a.pass], 1u);  // MODE 1/2: blockIdx.x
   __syncthreads();
 
@@ -493,7 +557,7 @@ OnesweepKernel(const PassArgs a) {
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {  // all loads first: the stores below may alias them as far as the compiler knows
       const uint32_t idx = i * THREADS + tid;
-      ck[i] = idx < tile_count ? LdStream(kin + idx) : 0u;
+      ck[i] = idx < tile_count ? KeyOut(KeyIn(LdStream(kin + idx), cin), cout) : 0u;
       if (KV) cv[i] = idx < tile_count ? LdStream(a.vals_in + tile_start + idx) : 0u;
     }
 #pragma unroll
@@ -515,12 +579,13 @@ OnesweepKernel(const PassArgs a) {
     const uint32_t* kin = a.keys_in + tile_start + woff;
     if (full) {
 #pragma unroll
-      for (int i = 0; i < IPT; ++i) key[i] = LdStream(kin + 32 * i);
+      for (int i = 0; i < IPT; ++i) key[i] = KeyIn(LdStream(kin + 32 * i), cin);
     } else {
-      // Tail tile: pad with the largest key so pads rank after every real key (the reference
+      // Tail tile: pad with the largest word so pads rank after every real key (the reference
       // pads the same way, downsweep.slang:81,85); their slots are >= tile_count and never stored.
 #pragma unroll
-      for (int i = 0; i < IPT; ++i) key[i] = (woff + 32 * i < tile_count) ? LdStream(kin + 32 * i) : 0xFFFFFFFFu;
+      for (int i = 0; i < IPT; ++i)
+        key[i] = (woff + 32 * i < tile_count) ? KeyIn(LdStream(kin + 32 * i), cin) : 0xFFFFFFFFu;
     }
   }
 
@@ -529,17 +594,18 @@ OnesweepKernel(const PassArgs a) {
   {
     uint32_t* cnt = s_cnt + warp * kRadix;
     const uint32_t lt = LaneMaskLt();
-    if (!KV && a.pass == 0) {
-      // Keys-only, first pass: there is no earlier order to preserve and equal keys are
-      // indistinguishable, so ANY bijective ranking inside a digit gives the same final output.
-      // The value returned by the atomic is such a ranking: no read-back, no collision repair.
-      // (Every later pass, and every pass of a key-value sort, must be stable.)
+    if (order_free && full) {
+      // Keys-only, first pass of a sort over all 32 bits: there is no earlier order to preserve
+      // and equal keys are indistinguishable, so ANY bijective ranking inside a digit gives the
+      // same final output.  The value returned by the atomic is such a ranking: no read-back, no
+      // collision repair.  (Every later pass, every pass of a key-value or bit-sub-range sort, and
+      // the tail tile — whose pads must keep ranking after the real keys — are stable.)
 #pragma unroll
-      for (int i = 0; i < IPT; ++i) rank[i] = atomicAdd(&cnt[(key[i] >> shift) & 0xFFu], 1u);
+      for (int i = 0; i < IPT; ++i) rank[i] = atomicAdd(&cnt[(key[i] >> shift) & mask], 1u);
     } else {
 #pragma unroll
       for (int i = 0; i < IPT; ++i) {
-        rank[i] = WarpRankDigit(cnt, (key[i] >> shift) & 0xFFu, lt);
+        rank[i] = WarpRankDigit(cnt, (key[i] >> shift) & mask, lt);
       }
     }
   }
@@ -555,8 +621,8 @@ OnesweepKernel(const PassArgs a) {
       wcount[w] = s_cnt[w * kRadix + tid];
       sum += wcount[w];
     }
-    // pads were counted as digit 255; they are not part of the data
-    digit_count = sum - ((tid == kRadix - 1) ? ((uint32_t)kTile - tile_count) : 0u);
+    // pads were counted as the largest digit of this pass; they are not part of the data
+    digit_count = sum - (((uint32_t)tid == mask) ? ((uint32_t)kTile - tile_count) : 0u);
     if (MODE != 1 && !unordered)
       StRelaxed(a.status + (size_t)tile * kRadix + tid,
                 (tile == 0 ? kStatusPrefix : kStatusAggregate) | digit_count);
@@ -607,7 +673,7 @@ OnesweepKernel(const PassArgs a) {
     const uint32_t* base = s_cnt + warp * kRadix;
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
-      const uint32_t d = (key[i] >> shift) & 0xFFu;
+      const uint32_t d = (key[i] >> shift) & mask;
       rank[i] += base[d];
       if (!Cfg::kPaired) s_keys[rank[i]] = key[i];
     }
@@ -651,16 +717,16 @@ OnesweepKernel(const PassArgs a) {
     const uint32_t slot = i * THREADS + tid;
     if (Cfg::kPaired) {
       const uint2 kv = reinterpret_cast<const uint2*>(s_keys)[slot];
-      const uint32_t g = s_gbase[(kv.x >> shift) & 0xFFu] + slot;
+      const uint32_t g = s_gbase[(kv.x >> shift) & mask] + slot;
       if (full || slot < tile_count) {
-        a.keys_out[g] = kv.x;
+        a.keys_out[g] = KeyOut(kv.x, cout);
         a.vals_out[g] = kv.y;
       }
     } else {
       const uint32_t k = s_keys[slot];
-      const uint32_t g = s_gbase[(k >> shift) & 0xFFu] + slot;
+      const uint32_t g = s_gbase[(k >> shift) & mask] + slot;
       if (full || slot < tile_count) {
-        a.keys_out[g] = k;
+        a.keys_out[g] = KeyOut(k, cout);
         if (KV) a.vals_out[g] = s_vals[slot];
       }
     }
@@ -877,8 +943,8 @@ constexpr int kUpsweepThreads = 256;
 
 template <int TILE>
 __global__ void __launch_bounds__(kUpsweepThreads)
-UpsweepKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t pass,
-              const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ tile_hist,
+UpsweepKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t shift, uint32_t mask,
+              const KeyCodec codec_in, const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ tile_hist,
               uint32_t* __restrict__ chunk_sums, StorageHeader* __restrict__ hdr, unsigned long long* ts_end) {
   constexpr int THREADS = kUpsweepThreads;
   static_assert(THREADS == kRadix, "one thread per digit");
@@ -894,7 +960,6 @@ UpsweepKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t
   if (blockIdx.x == 0 && tid == 0) hdr->hist_blocks_done = 0;  // counter of this pass's SpineScanKernel
   if (first >= tiles) return;
   const uint32_t last = first + kSpineChunk < tiles ? first + kSpineChunk : tiles;
-  const uint32_t shift = pass * kRadixBits;
   constexpr int kIters = (TILE + THREADS - 1) / THREADS;
   uint32_t chunk_acc = 0;
   __syncthreads();
@@ -909,12 +974,12 @@ UpsweepKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t
 #pragma unroll
       for (int i = 0; i < kIters; ++i) k[i] = LdStream(kin + i * THREADS + tid);
 #pragma unroll
-      for (int i = 0; i < kIters; ++i) atomicAdd(&hh[(k[i] >> shift) & 0xFFu], 1u);
+      for (int i = 0; i < kIters; ++i) atomicAdd(&hh[(KeyIn(k[i], codec_in) >> shift) & mask], 1u);
     } else {
 #pragma unroll
       for (int i = 0; i < kIters; ++i) {
         const uint32_t idx = i * THREADS + tid;
-        if (idx < tile_count) atomicAdd(&hh[(LdStream(kin + idx) >> shift) & 0xFFu], 1u);
+        if (idx < tile_count) atomicAdd(&hh[(KeyIn(LdStream(kin + idx), codec_in) >> shift) & mask], 1u);
       }
     }
     __syncthreads();  // one barrier per tile: the two histograms alternate
@@ -1291,6 +1356,37 @@ OnesweepTmaKernel(const PassArgs a) {
     // s_misc[8+slot] is next read two iterations from now, after several barriers
   }
   StampEnd(a.ts_end);
+}
+
+// CopyBackKernel — a sort with an odd number of passes (bit sub-range, extension) ends in the
+// scratch halves of the ping-pong; this moves [0, count) back into the caller's buffers and leaves
+// [count, max) untouched, like every pass does.  8 B/key (16 for pairs), grid-stride.
+__global__ void __launch_bounds__(256)
+CopyBackKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, const uint32_t* __restrict__ keys_src,
+               uint32_t* __restrict__ keys_dst, const uint32_t* __restrict__ vals_src, uint32_t* __restrict__ vals_dst,
+               unsigned long long* ts_end) {
+  GridDepLaunch();
+  GridDepWait();
+  const uint32_t n = ResolveCount(indirect, n_or_max);
+  const uint64_t stride = (uint64_t)gridDim.x * 256 * 4;
+  for (uint64_t base = (uint64_t)blockIdx.x * 256 * 4 + threadIdx.x; base < n; base += stride) {
+    uint32_t k[4], v[4];  // all loads first: four coalesced 1 KB rows in flight per CTA
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t i = base + (uint64_t)j * 256;
+      k[j] = (i < n) ? LdStream(keys_src + i) : 0u;
+      v[j] = (vals_src != nullptr && i < n) ? LdStream(vals_src + i) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t i = base + (uint64_t)j * 256;
+      if (i < n) {
+        keys_dst[i] = k[j];
+        if (vals_src != nullptr) vals_dst[i] = v[j];
+      }
+    }
+  }
+  StampEnd(ts_end);
 }
 
 }  // namespace vrdx

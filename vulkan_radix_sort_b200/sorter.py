@@ -118,6 +118,29 @@ class Sorter:
                                         query_pool, query)
         self.check()
 
+    def sort_ex(self, keys: torch.Tensor, values: torch.Tensor | None = None, *, key_type: int | None = None,
+                descending: bool = False, begin_bit: int = 0, end_bit: int = 32,
+                count_buffer: torch.Tensor | None = None, max_count: int | None = None, count_offset: int = 0,
+                storage: torch.Tensor | None = None, stream=None, query_pool=None, query: int = 0) -> None:
+        """``vrdxCudaCmdSortEx``: typed keys (uint32 / int32 / float32, inferred from the tensor dtype unless
+        given), ascending or descending, optional bit sub-range, optional payload, optional device count."""
+        if key_type is None:
+            key_type = {torch.float32: api.VRDX_CUDA_KEY_TYPE_FLOAT32, torch.int32: api.VRDX_CUDA_KEY_TYPE_INT32,
+                        torch.uint32: api.VRDX_CUDA_KEY_TYPE_UINT32}.get(keys.dtype)
+            if key_type is None:
+                raise TypeError(f"keys must be a 32-bit type, got {keys.dtype}")
+        k = keys.view(torch.int32) if keys.dtype != torch.int32 else keys
+        v = _as_i32(values) if values is not None else None
+        m = k.numel() if max_count is None else int(max_count)
+        st = storage if storage is not None else self.storage_for(m, v is not None)
+        info = api.make_key_info(key_type, api.VRDX_CUDA_SORT_ORDER_DESCENDING if descending
+                                 else api.VRDX_CUDA_SORT_ORDER_ASCENDING, begin_bit, end_bit)
+        api.vrdxCudaCmdSortEx(self._stream(stream), self.handle, info, m,
+                              count_buffer.data_ptr() if count_buffer is not None else None, count_offset,
+                              k.data_ptr(), 0, v.data_ptr() if v is not None else None, 0, st.data_ptr(), 0,
+                              query_pool, query)
+        self.check()
+
     @property
     def properties(self):
         return api.vrdxCudaGetSorterProperties(self.handle)
