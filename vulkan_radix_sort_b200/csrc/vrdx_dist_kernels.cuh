@@ -98,6 +98,51 @@ DistPrefixHistogramKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_
   }
 }
 
+// Class lookup by the top kDistLutBits bits of a key: if no splitter shares that prefix, every key
+// with it has the same class (2 * #splitters below it) and one byte-wide shared-memory load
+// classifies the key; otherwise (flag 0x80) the key needs the full comparison.  With 12 bits and 7
+// splitters 0.2 % of uniform keys take the slow path (an 8-bit table sent 2.7 % of the keys, i.e.
+// 58 % of the warp-instructions, there: 3.8 ms instead of 2.3 ms per 2^29 keys at 15 classes).
+constexpr int kDistLutBits = 12;
+constexpr int kDistLutSize = 1 << kDistLutBits;
+__device__ __forceinline__ void DistBuildClassLut(uint8_t* s_lut, const uint32_t* __restrict__ splitters,
+                                                  uint32_t splitter_count, int tid, int threads) {
+  // The table is a step function with at most splitter_count steps.  Step 1: every group of 16
+  // entries is filled with the value of its first entry (one 128-bit store per group).  Step 2:
+  // the <= splitter_count groups that contain a splitter's prefix are recomputed entry by entry,
+  // 16 threads per splitter (groups shared by several splitters get the same bytes twice).
+  for (uint32_t g = tid; g < (uint32_t)kDistLutSize / 16; g += threads) {
+    uint32_t below = 0;
+    for (uint32_t j = 0; j < splitter_count; ++j) below += (__ldg(splitters + j) >> (32 - kDistLutBits)) < g * 16;
+    const uint32_t v = 2u * below * 0x01010101u;
+    reinterpret_cast<uint4*>(s_lut)[g] = make_uint4(v, v, v, v);
+  }
+  __syncthreads();
+  for (uint32_t t = tid; t < 16 * splitter_count; t += threads) {
+    const uint32_t b = ((__ldg(splitters + (t >> 4)) >> (32 - kDistLutBits)) & ~15u) + (t & 15u);
+    uint32_t lo = 0, inside = 0;
+    for (uint32_t j = 0; j < splitter_count; ++j) {
+      const uint32_t ub = __ldg(splitters + j) >> (32 - kDistLutBits);
+      lo += ub < b;
+      inside |= ub == b;
+    }
+    s_lut[b] = (uint8_t)(inside ? 0x80u : 2u * lo);
+  }
+}
+
+// Full comparison of a key against the splitters.  Only keys whose top byte equals a splitter's top
+// byte get here (a few percent on any input that is not concentrated on the splitters), so the
+// loop is kept out of line: inlined at every use it made the kernel 5,700 instructions long and
+// instruction-fetch stalls its first limiter (profiles/kernels/k_dist_partition.txt).
+__device__ __noinline__ uint32_t DistClassOfSlow(uint32_t k, const uint32_t* s_u, uint32_t splitter_count) {
+  uint32_t gt = 0, eq = 0;
+  for (uint32_t j = 0; j < splitter_count; ++j) {
+    gt += k > s_u[j];
+    eq |= k == s_u[j];
+  }
+  return 2u * gt + eq;
+}
+
 // ---- class sizes (count only) ----------------------------------------------------------------------
 // Same class function as the multi-split below; warp-aggregated shared-memory counting (a class is
 // shared by many lanes, so peers are found with a ballot per class bit instead of colliding atomics).
@@ -105,30 +150,17 @@ __global__ void __launch_bounds__(kDistHistThreads)
 DistClassCountKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t splitter_count,
                      const uint32_t* __restrict__ splitters, uint32_t* __restrict__ counts) {
   __shared__ uint32_t s_u[kDistMaxSplitters];
-  __shared__ uint32_t s_top[kRadix];
+  __shared__ __align__(16) uint8_t s_top[kDistLutSize];
   __shared__ uint32_t s_cnt[32];
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid < (int)splitter_count) s_u[tid] = splitters[tid];
   if (tid < 32) s_cnt[tid] = 0;
-  if (tid < kRadix) {
-    uint32_t below = 0, inside = 0;
-    for (uint32_t j = 0; j < splitter_count; ++j) {
-      const uint32_t ub = splitters[j] >> 24;
-      below += ub < (uint32_t)tid;
-      inside |= ub == (uint32_t)tid;
-    }
-    s_top[tid] = inside ? 0x80000000u : 2u * below;
-  }
+  DistBuildClassLut(s_top, splitters, splitter_count, tid, kDistHistThreads);
   __syncthreads();
   auto class_of = [&](uint32_t k) -> uint32_t {
-    const uint32_t t = s_top[k >> 24];
-    if (!(t & 0x80000000u)) return t;
-    uint32_t gt = 0, eq = 0;
-    for (uint32_t j = 0; j < splitter_count; ++j) {
-      gt += k > s_u[j];
-      eq |= k == s_u[j];
-    }
-    return 2u * gt + eq;
+    const uint32_t t = s_top[k >> (32 - kDistLutBits)];
+    if (!(t & 0x80u)) return t;
+    return DistClassOfSlow(k, s_u, splitter_count);
   };
   auto count_class = [&](uint32_t c, bool valid) {
     // lanes of the warp holding class c: one atomic per (warp, class) group
@@ -195,9 +227,10 @@ DistPartitionKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t spli
   __shared__ uint32_t s_base[kDistClassSlots];         // tile-local first slot of each class
   __shared__ uint32_t s_gbase[kDistClassSlots];        // global slot of tile-local slot 0, per class
   __shared__ uint32_t s_keys[kDistPartTile];
-  __shared__ uint32_t s_top[kRadix];
+  __shared__ __align__(16) uint8_t s_top[kDistLutSize];
   __shared__ unsigned long long s_dptr[kDistMaxDests];
   __shared__ uint32_t s_dpos[kDistMaxDests + 1];
+  __shared__ uint32_t s_cdest[kDistClassSlots];        // SCATTER: destination that owns the first key of the class
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t tile_start = (uint64_t)blockIdx.x * kDistPartTile;
   if (tile_start >= n) return;
@@ -209,35 +242,19 @@ DistPartitionKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t spli
   const uint32_t tile_count = remaining < (uint32_t)kDistPartTile ? remaining : (uint32_t)kDistPartTile;
   if (tid < (int)splitter_count) s_u[tid] = splitters[tid];
   if (lane < kDistClassSlots) s_cnt[warp][lane] = 0;
-  {
-    // per top byte b: if no splitter has top byte b, every key with that byte has the same class
-    // (2 * #splitters below it); otherwise the key needs the full comparison (flag in bit 31)
-    const uint32_t b = tid;  // kDistPartThreads == 256
-    uint32_t below = 0, inside = 0;
-    for (uint32_t j = 0; j < splitter_count; ++j) {
-      const uint32_t ub = splitters[j] >> 24;
-      below += ub < b;
-      inside |= ub == b;
-    }
-    s_top[b] = inside ? 0x80000000u : 2u * below;
-  }
+  DistBuildClassLut(s_top, splitters, splitter_count, tid, kDistPartThreads);
   __syncthreads();
   auto class_of = [&](uint32_t k) -> uint32_t {
-    const uint32_t t = s_top[k >> 24];
-    if (!(t & 0x80000000u)) return t;
-    uint32_t gt = 0, eq = 0;
-    for (uint32_t j = 0; j < splitter_count; ++j) {
-      gt += k > s_u[j];
-      eq |= k == s_u[j];
-    }
-    return 2u * gt + eq;
+    const uint32_t t = s_top[k >> (32 - kDistLutBits)];
+    if (!(t & 0x80u)) return t;
+    return DistClassOfSlow(k, s_u, splitter_count);
   };
 
   const uint32_t lt = LaneMaskLt();
   const uint32_t woff = warp * 32 * kDistPartItems + lane;
   const uint32_t* kin = keys + tile_start + woff;
   uint32_t key[kDistPartItems], rank[kDistPartItems];
-  uint8_t cls[kDistPartItems];
+  uint32_t cls[kDistPartItems / 4] = {};  // four 8-bit class labels per register
 #pragma unroll
   for (int i = 0; i < kDistPartItems; ++i)
     key[i] = (woff + 32 * i < tile_count) ? LdStream(kin + 32 * i) : 0xFFFFFFFFu;
@@ -246,7 +263,7 @@ DistPartitionKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t spli
     const bool valid = woff + 32 * i < tile_count;
     // invalid (pad) lanes take the unused top slot so that they rank after every real key
     const uint32_t c = valid ? class_of(key[i]) : (uint32_t)(kDistClassSlots - 1);
-    cls[i] = (uint8_t)c;
+    cls[i >> 2] |= c << (8 * (i & 3));
     uint32_t peers = 0xffffffffu;
 #pragma unroll
     for (int b = 0; b < 5; ++b) {
@@ -276,11 +293,16 @@ DistPartitionKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t spli
     const bool real = tid < (int)(2 * splitter_count + 1);
     const uint32_t g = (real && sum) ? atomicAdd(&cursors[tid], sum) : 0u;
     s_gbase[tid] = g - excl;
+    if (SCATTER) {
+      uint32_t j = 0;
+      for (uint32_t d = 1; d < dest_count; ++d) j += g >= s_dpos[d];
+      s_cdest[tid] = j;
+    }
   }
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < kDistPartItems; ++i) {
-    const uint32_t c = cls[i];
+    const uint32_t c = (cls[i >> 2] >> (8 * (i & 3))) & 0xFFu;
     rank[i] += s_cnt[warp][c] + s_base[c];
     s_keys[rank[i]] = key[i];
   }
@@ -291,12 +313,16 @@ DistPartitionKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t spli
     const uint32_t slot = i * kDistPartThreads + tid;
     if (slot < tile_count) {
       const uint32_t k = s_keys[slot];
-      const uint32_t p = s_gbase[class_of(k)] + slot;  // class-ordered position among the local keys
+      const uint32_t c = class_of(k);
+      const uint32_t p = s_gbase[c] + slot;  // class-ordered position among the local keys
       if (!SCATTER) {
         out[p] = k;
       } else {
-        uint32_t j = 0;
-        for (uint32_t d = 1; d < dest_count; ++d) j += p >= s_dpos[d];
+        // the keys a tile adds to one class almost always land in one destination; a class that is
+        // split between destinations (ties on a splitter) walks on from there
+        uint32_t j = s_cdest[c];
+#pragma unroll 1
+        while (j + 1 < dest_count && p >= s_dpos[j + 1]) ++j;
         reinterpret_cast<uint32_t*>(s_dptr[j])[p - s_dpos[j]] = k;
       }
     }
