@@ -81,6 +81,46 @@ def test_partition_groups_by_class(backends, dist_name):
             assert np.array_equal(np.sort(got[a:a + sz]), np.sort(k[cls == c])), (dist_name, n, c)
 
 
+@pytest.mark.parametrize("n", [4099, 300_007, (1 << 21) + 3])
+def test_partition_scatter_to_eight_destinations_on_one_gpu(backends, n):
+    """The fused partition + exchange kernel with the table an 8-GPU run builds, all eight "peers" being regions of
+    one local buffer: destination boundaries at class edges, inside tie classes (twice inside the same one) and an
+    empty destination.  Any order inside a class is legal, so regions are compared as multisets."""
+    cuda_b, _ = backends
+    rng = np.random.default_rng(n)
+    k = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    k[rng.random(n) < 0.2] = 0x40000000          # a heavy tie on one splitter
+    k[rng.random(n) < 0.05] = 0xFFFFFFFF         # ties on the largest key
+    k[rng.random(n) < 0.01] = 5
+    splitters = [5, 1000, 0x40000000, 0x80000000, 0xC0000000, 0xFFFFFFF0, 0xFFFFFFFF]
+    u = np.array(splitters, dtype=np.uint64)
+    k64 = k.astype(np.uint64)
+    cls = 2 * (k64[:, None] > u[None, :]).sum(axis=1) + (k64[:, None] == u[None, :]).any(axis=1)
+    sizes = np.bincount(cls, minlength=2 * len(splitters) + 1)
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    tie = 5                                       # class of keys == 0x40000000
+    cuts = sorted({0, int(starts[2]), int(starts[tie] + sizes[tie] // 3), int(starts[tie] + 2 * sizes[tie] // 3),
+                   int(starts[8]), int(starts[11]), int(starts[13] + sizes[13] // 2)})
+    first_pos = cuts[:5] + [cuts[4]] + cuts[5:] + [n]      # destination 4 is empty
+    assert len(first_pos) == 9 and first_pos == sorted(first_pos)
+    gap = 64                                      # guard words between the regions: nothing may be written there
+    region_off = [fp + gap * (j + 1) for j, fp in enumerate(first_pos[:8])]
+    out = torch.full((n + gap * 10,), 0x5A5A5A5A, dtype=torch.int32, device="cuda")
+    dest_ptrs = [out.data_ptr() + 4 * off for off in region_off]
+    cuda_b.partition_scatter(_dev(k), n, torch.tensor(splitters, dtype=torch.int64, device="cuda"),
+                             torch.tensor(starts[:-1], dtype=torch.int64, device="cuda"), dest_ptrs, first_pos)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().view(np.uint32)
+    ordered = np.sort(k)                          # class order == key order, so position p holds ordered[p] up to ties
+    written = np.zeros(got.size, dtype=bool)
+    for j in range(8):
+        a, b = first_pos[j], first_pos[j + 1]
+        region = got[region_off[j]: region_off[j] + (b - a)]
+        written[region_off[j]: region_off[j] + (b - a)] = True
+        assert np.array_equal(np.sort(region), ordered[a:b]), (n, j)
+    assert np.all(got[~written] == 0x5A5A5A5A)    # guards and slack untouched
+
+
 def _nccl_worker(rank, world, port, dist_name, n, q, fused=False, strategy="exact"):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
