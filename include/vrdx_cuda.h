@@ -102,6 +102,18 @@ void vrdxCudaCmdSortEx(VkCommandBuffer commandBuffer, VrdxSorter sorter,
                        VkBuffer storageBuffer, VkDeviceSize storageOffset, VkQueryPool queryPool,
                        uint32_t query);
 
+/* 64-bit keys (keys only).  keyType is read as its 64-bit counterpart (UINT32 -> uint64, INT32 ->
+ * int64, FLOAT32 -> float64 / double, same total order rules), order as above; beginBit / endBit
+ * are ignored (all 64 bits are compared).  Implemented as two chained 32-bit key-value sorts (low
+ * word, then high word), so it needs its own, larger storage: vrdxCudaGetSorterKeys64Storage-
+ * Requirements.  The keys buffer + offset must be 8-byte aligned.  indirectBuffer NULL = direct. */
+void vrdxCudaGetSorterKeys64StorageRequirements(VrdxSorter sorter, uint32_t maxElementCount,
+                                                VrdxSorterStorageRequirements* requirements);
+void vrdxCudaCmdSortKeys64(VkCommandBuffer commandBuffer, VrdxSorter sorter,
+                           const VrdxCudaSortKeyInfo* pKeyInfo, uint32_t elementCount,
+                           VkBuffer indirectBuffer, VkDeviceSize indirectOffset, VkBuffer keysBuffer,
+                           VkDeviceSize keysOffset, VkBuffer storageBuffer, VkDeviceSize storageOffset);
+
 /* ------------------------------------------------------------------ error channel */
 
 /* Last CUDA error (cudaError_t as int, 0 = none) raised by any vrdxCmd* on this sorter since

@@ -153,6 +153,22 @@ def sort_ex(bits: np.ndarray, values=None, key_type: int = KEY_UINT32, descendin
     return b[perm], (None if values is None else np.ascontiguousarray(values).view(np.uint32)[perm])
 
 
+def sort_keys64(bits: np.ndarray, key_type: int = KEY_UINT32, descending: bool = False) -> np.ndarray:
+    """64-bit counterpart of sort_ex (keys only): sort by the order-preserving unsigned image of the 64-bit
+    pattern (KEY_INT32 / KEY_FLOAT32 stand for int64 / float64).  Returns the raw uint64 patterns in order."""
+    b = np.ascontiguousarray(bits).view(np.uint64)
+    top = np.uint64(1) << np.uint64(63)
+    if key_type == KEY_INT32:
+        t = b ^ top
+    elif key_type == KEY_FLOAT32:
+        t = np.where((b >> np.uint64(63)).astype(bool), ~b, b ^ top).astype(np.uint64)
+    else:
+        t = b.copy()
+    if descending:
+        t = ~t
+    return b[np.argsort(t, kind="stable")]
+
+
 def is_sorted(keys: np.ndarray) -> bool:
     k = np.ascontiguousarray(keys, dtype=np.uint32)
     return bool(oracle_lib().vrdx_oracle_is_sorted(_ptr(k), k.size))

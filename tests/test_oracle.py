@@ -180,3 +180,20 @@ def test_sort_ex_bit_range_is_a_stable_field_sort(oracle):
         assert np.array_equal(u[p], k)
     k, p = oracle.sort_ex(u, v, begin_bit=7, end_bit=7)
     assert np.array_equal(k, u) and np.array_equal(p, v)               # empty range: nothing moves
+
+
+def test_sort_keys64_matches_numpy_typed_sorts(oracle):
+    rng = np.random.default_rng(13)
+    u = rng.integers(0, 1 << 64, 30_000, dtype=np.uint64)
+    u[::7] &= np.uint64(0xFFFFFFFF)                     # equal high words: the low word decides
+    u[1::7] &= np.uint64(0xFFFFFFFF00000000)            # equal low words
+    assert np.array_equal(oracle.sort_keys64(u), np.sort(u))
+    i = u.view(np.int64)
+    assert np.array_equal(oracle.sort_keys64(i, key_type=oracle.KEY_INT32).view(np.int64), np.sort(i))
+    assert np.array_equal(oracle.sort_keys64(i, key_type=oracle.KEY_INT32, descending=True).view(np.int64), np.sort(i)[::-1])
+    f = rng.standard_normal(30_000) * 1e6
+    f[::11] = np.inf
+    f[1::13] = -np.inf
+    f[2::17] = 5e-324                                    # subnormal
+    assert np.array_equal(oracle.sort_keys64(f, key_type=oracle.KEY_FLOAT32).view(np.float64), np.sort(f))
+    assert np.array_equal(oracle.sort_keys64(f, key_type=oracle.KEY_FLOAT32, descending=True).view(np.float64), np.sort(f)[::-1])

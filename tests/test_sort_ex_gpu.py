@@ -164,3 +164,52 @@ def test_tail_tile_real_keys_with_the_pad_digit_are_not_dropped(algorithm, oracl
                 assert np.array_equal(w.cpu().numpy().view(np.uint32), np.sort(k)), (algorithm, tail)
     finally:
         s.close()
+
+
+# ---- 64-bit keys (two chained key-value sorts: low word, then high word)
+
+def _bits64(kind, n, seed):
+    rng = np.random.default_rng(seed)
+    if kind == "float64":
+        f = rng.standard_normal(n) * 1e6
+        f[::11] = np.inf
+        f[1::13] = -np.inf
+        f[2::17] = 5e-324
+        f[3::19] = 0.0
+        f[4::23] = -0.0
+        f[5::29] = np.nan
+        return f.view(np.uint64).copy()
+    u = rng.integers(0, 1 << 64, n, dtype=np.uint64)
+    u[::7] &= np.uint64(0xFFFFFFFF)
+    u[1::7] &= np.uint64(0xFFFFFFFF00000000)
+    u[2::7] = u[0]                                        # exact duplicates
+    return u
+
+
+@pytest.mark.parametrize("n", [1, 4097, 300_007, 5_000_001])
+@pytest.mark.parametrize("kind", ["uint64", "int64", "float64"])
+@pytest.mark.parametrize("descending", [False, True])
+def test_keys64_bit_exact(sorter, oracle, n, kind, descending):
+    bits = _bits64(kind, n, n)
+    kt = {"uint64": 0, "int64": 1, "float64": 2}[kind]
+    want = oracle.sort_keys64(bits, key_type=kt, descending=descending)
+    d = torch.from_numpy(bits.view(np.int64).copy()).to(DEV)
+    sorter.sort_keys64(d, key_type=kt, descending=descending)
+    torch.cuda.synchronize()
+    assert np.array_equal(d.cpu().numpy().view(np.uint64), want)
+
+
+def test_keys64_typed_tensors_and_indirect_count(any_sorter, oracle):
+    g = torch.Generator(device="cpu").manual_seed(3)
+    f = torch.randn(400_003, generator=g, dtype=torch.float64).to(DEV)
+    mine = f.clone()
+    any_sorter.sort_keys64(mine)
+    assert torch.equal(mine, torch.sort(f).values)
+    i = torch.randint(-2**62, 2**62, (400_003,), generator=g, dtype=torch.int64).to(DEV)
+    count = 250_001
+    cnt = torch.tensor([count], dtype=torch.int32, device=DEV)
+    mine = i.clone()
+    any_sorter.sort_keys64(mine, descending=True, count_buffer=cnt, max_count=i.numel())
+    torch.cuda.synchronize()
+    assert torch.equal(mine[:count], torch.sort(i[:count], descending=True).values)
+    assert torch.equal(mine[count:], i[count:])            # tail untouched

@@ -96,6 +96,9 @@ _SIGNATURES = {
     "vrdxCudaGetSorterProperties": (None, [c_void_p, POINTER(VrdxCudaSorterProperties)]),
     "vrdxCudaCmdSortEx": (None, [c_void_p, c_void_p, POINTER(VrdxCudaSortKeyInfo), c_uint32, c_void_p, c_uint64,
                                  c_void_p, c_uint64, c_void_p, c_uint64, c_void_p, c_uint64, c_void_p, c_uint32]),
+    "vrdxCudaGetSorterKeys64StorageRequirements": (None, [c_void_p, c_uint32, POINTER(VrdxSorterStorageRequirements)]),
+    "vrdxCudaCmdSortKeys64": (None, [c_void_p, c_void_p, POINTER(VrdxCudaSortKeyInfo), c_uint32, c_void_p, c_uint64,
+                                     c_void_p, c_uint64, c_void_p, c_uint64]),
     "vrdxCudaImportSemaphoreFd": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p)]),
     "vrdxCudaCmdWaitSemaphore": (c_int, [c_void_p, c_void_p, c_uint64]),
     "vrdxCudaCmdSignalSemaphore": (c_int, [c_void_p, c_void_p, c_uint64]),
@@ -262,6 +265,19 @@ def vrdxCudaCmdSortEx(command_buffer, sorter, key_info, element_count, indirect_
                                      element_count, indirect_buffer, indirect_offset, keys_buffer, keys_offset,
                                      values_buffer, values_offset, storage_buffer, storage_offset, query_pool,
                                      query)
+
+
+def vrdxCudaGetSorterKeys64StorageRequirements(sorter, max_element_count: int) -> VrdxSorterStorageRequirements:
+    req = VrdxSorterStorageRequirements()
+    load_library().vrdxCudaGetSorterKeys64StorageRequirements(sorter, max_element_count, byref(req))
+    return req
+
+
+def vrdxCudaCmdSortKeys64(command_buffer, sorter, key_info, element_count, indirect_buffer, indirect_offset,
+                          keys_buffer, keys_offset, storage_buffer, storage_offset) -> None:
+    load_library().vrdxCudaCmdSortKeys64(command_buffer, sorter, byref(key_info) if key_info is not None else None,
+                                         element_count, indirect_buffer, indirect_offset, keys_buffer, keys_offset,
+                                         storage_buffer, storage_offset)
 
 
 def vrdxCudaGetSorterProperties(sorter) -> VrdxCudaSorterProperties:

@@ -836,6 +836,79 @@ void vrdxCudaReleaseImportedMemory(VrdxCudaImportedMemory memory) {
   delete memory;
 }
 
+void vrdxCudaGetSorterKeys64StorageRequirements(VrdxSorter /*sorter*/, uint32_t maxElementCount,
+                                                VrdxSorterStorageRequirements* requirements) {
+  if (!requirements) return;
+  const StorageLayout lay = ComputeLayout(maxElementCount, kMinTile);
+  // lo[] | hi[] | storage of a key-value sort
+  requirements->size = 2 * AlignUp((uint64_t)maxElementCount * sizeof(uint32_t), (uint64_t)kOffsetAlignment) + lay.total_kv;
+  requirements->usage = VK_BUFFER_USAGE_STORAGE_BUFFER_BIT | VK_BUFFER_USAGE_TRANSFER_DST_BIT;
+}
+
+void vrdxCudaCmdSortKeys64(VkCommandBuffer commandBuffer, VrdxSorter sorter, const VrdxCudaSortKeyInfo* pKeyInfo,
+                           uint32_t elementCount, VkBuffer indirectBuffer, VkDeviceSize indirectOffset,
+                           VkBuffer keysBuffer, VkDeviceSize keysOffset, VkBuffer storageBuffer,
+                           VkDeviceSize storageOffset) {
+  if (!sorter) return;
+  KeyCodec64 codec{0ull, 0ull, 0ull};
+  if (pKeyInfo) {
+    if (pKeyInfo->structSize < sizeof(VrdxCudaSortKeyInfo) ||
+        (uint32_t)pKeyInfo->keyType > (uint32_t)VRDX_CUDA_KEY_TYPE_FLOAT32 ||
+        (uint32_t)pKeyInfo->order > (uint32_t)VRDX_CUDA_SORT_ORDER_DESCENDING) {
+      NoteError(sorter, cudaErrorInvalidValue);
+      return;
+    }
+    codec.cmask = pKeyInfo->keyType == VRDX_CUDA_KEY_TYPE_UINT32 ? 0ull : 0x8000000000000000ull;
+    codec.fmask = pKeyInfo->keyType == VRDX_CUDA_KEY_TYPE_FLOAT32 ? 0x7FFFFFFFFFFFFFFFull : 0ull;
+    codec.dmask = pKeyInfo->order == VRDX_CUDA_SORT_ORDER_DESCENDING ? ~0ull : 0ull;
+  }
+  char* keys = keysBuffer ? reinterpret_cast<char*>(keysBuffer) + keysOffset : nullptr;
+  char* storage = storageBuffer ? reinterpret_cast<char*>(storageBuffer) + storageOffset : nullptr;
+  if (elementCount == 0) {
+    sorter->last_launches.store(0);
+    return;
+  }
+  if (!keys || !storage || (reinterpret_cast<uintptr_t>(keys) & 7u) || (reinterpret_cast<uintptr_t>(storage) & 3u)) {
+    NoteError(sorter, cudaErrorInvalidValue);
+    return;
+  }
+  const uint32_t* indirect =
+      indirectBuffer ? reinterpret_cast<const uint32_t*>(reinterpret_cast<char*>(indirectBuffer) + indirectOffset) : nullptr;
+  const uint64_t half = AlignUp((uint64_t)elementCount * sizeof(uint32_t), (uint64_t)kOffsetAlignment);
+  uint32_t* lo = reinterpret_cast<uint32_t*>(storage);
+  uint32_t* hi = reinterpret_cast<uint32_t*>(storage + half);
+  char* inner = storage + 2 * half;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(commandBuffer);
+  uint32_t launches = 0;
+  {
+    DeviceGuard guard(sorter->device);
+    const uint64_t blocks = CeilDiv((uint64_t)elementCount, (uint64_t)1024);
+    const uint64_t cap = (uint64_t)sorter->sm_count * 8;
+    const uint32_t grid = (uint32_t)(blocks < cap ? blocks : cap);
+    NoteError(sorter, LaunchEx(Split64Kernel, grid, 256u, 0, stream, false, indirect, elementCount,
+                               reinterpret_cast<const unsigned long long*>(keys), lo, hi, codec));
+    ++launches;
+  }
+  // stable by the low word (payload: high word), then stable by the high word (payload: low word)
+  EnqueueSort(commandBuffer, sorter, elementCount, indirectBuffer, indirectOffset, reinterpret_cast<VkBuffer>(lo), 0,
+              reinterpret_cast<VkBuffer>(hi), 0, reinterpret_cast<VkBuffer>(inner), 0, VK_NULL_HANDLE, 0);
+  launches += sorter->last_launches.load();
+  EnqueueSort(commandBuffer, sorter, elementCount, indirectBuffer, indirectOffset, reinterpret_cast<VkBuffer>(hi), 0,
+              reinterpret_cast<VkBuffer>(lo), 0, reinterpret_cast<VkBuffer>(inner), 0, VK_NULL_HANDLE, 0);
+  launches += sorter->last_launches.load();
+  {
+    DeviceGuard guard(sorter->device);
+    const uint64_t blocks = CeilDiv((uint64_t)elementCount, (uint64_t)1024);
+    const uint64_t cap = (uint64_t)sorter->sm_count * 8;
+    const uint32_t grid = (uint32_t)(blocks < cap ? blocks : cap);
+    NoteError(sorter, LaunchEx(Merge64Kernel, grid, 256u, 0, stream, false, indirect, elementCount,
+                               (const uint32_t*)lo, (const uint32_t*)hi, reinterpret_cast<unsigned long long*>(keys),
+                               codec));
+    ++launches;
+  }
+  sorter->last_launches.store(launches);
+}
+
 VkResult vrdxCudaImportSemaphoreFd(VkDevice device, int fd, int timeline, VrdxCudaImportedSemaphore* pSemaphore) {
   if (!pSemaphore || fd < 0) return VK_ERROR_INITIALIZATION_FAILED;
   const int dev = DeviceFromHandle(device);

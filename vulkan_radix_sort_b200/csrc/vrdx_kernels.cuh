@@ -1389,4 +1389,69 @@ CopyBackKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, const u
   StampEnd(ts_end);
 }
 
+// ------------------------------------------------------------------------------------------
+// 64-bit keys by composition (extension; the reference has 32-bit keys only).  An LSD sort of 64-bit
+// words is a stable sort by the low word followed by a stable sort by the high word, and each of
+// those is exactly the key-value sort above with the other half of the word as the payload:
+//   Split64Kernel   keys64 -> lo[], hi[]   (applies the order-preserving codec of the key type)
+//   key-value sort (key = lo, value = hi); key-value sort (key = hi, value = lo)
+//   Merge64Kernel   lo[], hi[] -> keys64   (undoes the codec)
+// 168 B/key moved instead of the 136 B/key of a native 8-pass 64-bit sort, with no new tile kernel.
+// ------------------------------------------------------------------------------------------
+struct KeyCodec64 {
+  unsigned long long fmask, cmask, dmask;  // float64: f = 0x7FF..F, c = 0x800..0; int64: c only; descending: d = ~0
+};
+__device__ __forceinline__ unsigned long long KeyIn64(unsigned long long k, const KeyCodec64 c) {
+  return k ^ ((unsigned long long)((long long)k >> 63) & c.fmask) ^ (c.cmask ^ c.dmask);
+}
+__device__ __forceinline__ unsigned long long KeyOut64(unsigned long long t, const KeyCodec64 c) {
+  const unsigned long long u = t ^ c.dmask;
+  return u ^ ((unsigned long long)(~(long long)u >> 63) & c.fmask) ^ c.cmask;
+}
+
+__global__ void __launch_bounds__(256)
+Split64Kernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, const unsigned long long* __restrict__ keys,
+              uint32_t* __restrict__ lo, uint32_t* __restrict__ hi, const KeyCodec64 codec) {
+  const uint32_t n = ResolveCount(indirect, n_or_max);
+  const uint64_t stride = (uint64_t)gridDim.x * 256 * 4;
+  for (uint64_t base = (uint64_t)blockIdx.x * 256 * 4 + threadIdx.x; base < n; base += stride) {
+    unsigned long long k[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t i = base + (uint64_t)j * 256;
+      k[j] = (i < n) ? __ldcs(keys + i) : 0ull;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t i = base + (uint64_t)j * 256;
+      if (i < n) {
+        const unsigned long long t = KeyIn64(k[j], codec);
+        lo[i] = (uint32_t)t;
+        hi[i] = (uint32_t)(t >> 32);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+Merge64Kernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, const uint32_t* __restrict__ lo,
+              const uint32_t* __restrict__ hi, unsigned long long* __restrict__ keys, const KeyCodec64 codec) {
+  const uint32_t n = ResolveCount(indirect, n_or_max);
+  const uint64_t stride = (uint64_t)gridDim.x * 256 * 4;
+  for (uint64_t base = (uint64_t)blockIdx.x * 256 * 4 + threadIdx.x; base < n; base += stride) {
+    uint32_t l[4], h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t i = base + (uint64_t)j * 256;
+      l[j] = (i < n) ? LdStream(lo + i) : 0u;
+      h[j] = (i < n) ? LdStream(hi + i) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t i = base + (uint64_t)j * 256;
+      if (i < n) keys[i] = KeyOut64(((unsigned long long)h[j] << 32) | l[j], codec);
+    }
+  }
+}
+
 }  // namespace vrdx

@@ -141,6 +141,29 @@ class Sorter:
                               query_pool, query)
         self.check()
 
+    def sort_keys64(self, keys: torch.Tensor, *, key_type: int | None = None, descending: bool = False,
+                    count_buffer: torch.Tensor | None = None, max_count: int | None = None, count_offset: int = 0,
+                    storage: torch.Tensor | None = None, stream=None) -> None:
+        """``vrdxCudaCmdSortKeys64``: 64-bit keys (int64 / uint64 / float64 tensor), keys only, in place."""
+        if key_type is None:
+            key_type = {torch.float64: api.VRDX_CUDA_KEY_TYPE_FLOAT32, torch.int64: api.VRDX_CUDA_KEY_TYPE_INT32,
+                        torch.uint64: api.VRDX_CUDA_KEY_TYPE_UINT32}.get(keys.dtype)
+        if key_type is None or keys.element_size() != 8:
+            raise TypeError(f"keys must be a 64-bit type, got {keys.dtype}")
+        m = keys.numel() if max_count is None else int(max_count)
+        if storage is None:
+            need = int(api.vrdxCudaGetSorterKeys64StorageRequirements(self.handle, m).size)
+            if self._storage is None or self._storage.numel() < need:
+                self._storage = None
+                self._storage = torch.empty(need, dtype=torch.uint8, device=self.device)
+            storage = self._storage
+        info = api.make_key_info(key_type, api.VRDX_CUDA_SORT_ORDER_DESCENDING if descending
+                                 else api.VRDX_CUDA_SORT_ORDER_ASCENDING)
+        api.vrdxCudaCmdSortKeys64(self._stream(stream), self.handle, info, m,
+                                  count_buffer.data_ptr() if count_buffer is not None else None, count_offset,
+                                  keys.data_ptr(), 0, storage.data_ptr(), 0)
+        self.check()
+
     @property
     def properties(self):
         return api.vrdxCudaGetSorterProperties(self.handle)
