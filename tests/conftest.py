@@ -33,14 +33,18 @@ def sorter():
 
 
 FLAVOURS = {
-    # name: (algorithm, tile_load, reserved variant selectors)
+    # name: (algorithm, tile_load, reserved selectors: [0] keys shape + 1, [1] key-value shape + 1, [2] experiment)
     "onesweep": ("ONESWEEP", "DIRECT", None),
     "reduce_then_scan": ("REDUCE_THEN_SCAN", "DIRECT", None),
-    "onesweep_tma_persistent": ("ONESWEEP", "TMA", None),
-    "reduce_then_scan_tma_persistent": ("REDUCE_THEN_SCAN", "TMA", None),
-    "onesweep_cluster4_lookback": ("ONESWEEP", "DIRECT", (6, 6)),   # kKeysVariants[5] / kPairVariants[5]
-    "reduce_then_scan_paired_staging": ("REDUCE_THEN_SCAN", "DIRECT", (0, 0, 0, 0, 9)),  # k*Variants[8]
     "auto": ("AUTO", "AUTO", None),
+    # alternate tile shapes compiled into the product library (kKeysShapes / kPairShapes in csrc/vrdx_api.cu)
+    "onesweep_256x16": ("ONESWEEP", "DIRECT", (2, 2)),
+    "reduce_then_scan_512x16": ("REDUCE_THEN_SCAN", "DIRECT", (5, 5)),
+    # losing variants, only in libraries built with VRDX_EXPERIMENTS=1 (skipped on the product library)
+    "x_onesweep_tma_persistent": ("ONESWEEP", "TMA", None),
+    "x_reduce_then_scan_tma_persistent": ("REDUCE_THEN_SCAN", "TMA", None),
+    "x_onesweep_cluster4_lookback": ("ONESWEEP", "DIRECT", (0, 0, 2)),
+    "x_round1_tile_kernel": ("AUTO", "DIRECT", (0, 0, 1)),
 }
 
 
@@ -52,8 +56,13 @@ def any_sorter(request):
         pytest.skip("no CUDA device")
     from vulkan_radix_sort_b200 import Sorter, api
     algo, load, reserved = FLAVOURS[request.param]
-    s = Sorter(0, algorithm=getattr(api, "VRDX_CUDA_ALGORITHM_" + algo),
-               tile_load=getattr(api, "VRDX_CUDA_TILE_LOAD_" + load), reserved=reserved)
+    try:
+        s = Sorter(0, algorithm=getattr(api, "VRDX_CUDA_ALGORITHM_" + algo),
+                   tile_load=getattr(api, "VRDX_CUDA_TILE_LOAD_" + load), reserved=reserved)
+    except RuntimeError as e:
+        if request.param.startswith("x_") and str(api.VK_ERROR_FEATURE_NOT_PRESENT) in str(e):
+            pytest.skip("experimental variant: not in the product library (build with VRDX_EXPERIMENTS=1)")
+        raise
     s.kind = request.param
     yield s
     s.close()

@@ -133,9 +133,9 @@ def load_library() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if not os.path.exists(path):
-        path = _build.build()
+    # (re)build if the library is missing or older than csrc/ or include/ (no silent stale library);
+    # a VRDX_LIB override is loaded as it is
+    path = _build.LIB_PATH if os.environ.get("VRDX_LIB") else _build.build()
     lib = ctypes.CDLL(path)
     for name, (restype, argtypes) in _SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
@@ -161,8 +161,9 @@ def vrdxCreateSorter(create_info: VrdxSorterCreateInfo):
 
 def vrdxCudaCreateSorter(create_info: VrdxSorterCreateInfo, algorithm=VRDX_CUDA_ALGORITHM_AUTO,
                          tile_load=VRDX_CUDA_TILE_LOAD_AUTO, reserved=None):
-    """``reserved``: optional kernel-variant selectors for A/B runs (index + 1; 0 = default):
-    [0] keys onesweep, [1] pairs onesweep, [2] keys TMA, [3] pairs TMA, [4] reduce-then-scan."""
+    """``reserved``: optional tile-shape selectors for A/B runs (index + 1; 0 = default):
+    [0] keys-only shape, [1] key-value shape (both algorithms), [2] experiment id (libraries built with
+    -DVRDX_EXPERIMENTS only; the product library answers VK_ERROR_FEATURE_NOT_PRESENT)."""
     opts = VrdxCudaSorterOptions()
     opts.structSize = ctypes.sizeof(VrdxCudaSorterOptions)
     opts.algorithm = algorithm

@@ -41,28 +41,45 @@ def needs_build() -> bool:
     return (not os.path.exists(LIB_PATH)) or os.path.getmtime(LIB_PATH) < _newest_source_mtime()
 
 
-def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
-    """Compile the library if it is missing or older than its sources. Returns its path."""
-    if not force and not needs_build():
-        return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [
-        _nvcc(), "-O3", "-std=c++17", *ARCH_FLAGS, "-lineinfo",
-        "-Xcompiler", "-fPIC,-O2,-Wall", "-shared",
-        "-I", INCLUDE, "-I", CSRC,
-        *extra_flags,
-        "-o", LIB_PATH,
-        *[os.path.join(CSRC, s) for s in SOURCES],
-    ]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd), flush=True)
-    out = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or out.returncode != 0:
-        sys.stderr.write(out.stdout + out.stderr)
-    if out.returncode != 0:
-        raise RuntimeError("nvcc failed building libvrdx_b200.so")
-    return LIB_PATH
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out_path: str | None = None) -> str:
+    """Compile the library if it is missing or older than its sources. Returns its path.
+
+    Safe to call from several processes at once (one rank per GPU): the compile runs under a file
+    lock, into a temporary file that is renamed over the target, so nobody can dlopen a half-written
+    library and only the first caller pays for the compile.
+    `out_path` + `extra_flags` build an A/B copy of the same ABI (load it with VRDX_LIB=path)."""
+    target = out_path or LIB_PATH
+    if out_path is None and not force and not needs_build():
+        return target
+    os.makedirs(os.path.dirname(target), exist_ok=True)
+    import fcntl
+    with open(target + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if out_path is None and not force and not needs_build():
+            return target  # another process built it while we waited
+        if os.environ.get("VRDX_EXPERIMENTS") == "1":
+            extra_flags = (*extra_flags, "-DVRDX_EXPERIMENTS")
+        tmp = f"{target}.{os.getpid()}.tmp"
+        cmd = [
+            _nvcc(), "-O3", "-std=c++17", *ARCH_FLAGS, "-lineinfo",
+            "-Xcompiler", "-fPIC,-O2,-Wall", "-shared",
+            "-I", INCLUDE, "-I", CSRC,
+            *extra_flags,
+            "-o", tmp,
+            *[os.path.join(CSRC, s) for s in SOURCES],
+        ]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd), flush=True)
+        out = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or out.returncode != 0:
+            sys.stderr.write(out.stdout + out.stderr)
+        if out.returncode != 0:
+            if os.path.exists(tmp):
+                os.unlink(tmp)
+            raise RuntimeError("nvcc failed building libvrdx_b200.so")
+        os.replace(tmp, target)
+    return target
 
 
 if __name__ == "__main__":

@@ -30,30 +30,21 @@ using namespace vrdx;
 
 // ---------------------------------------------------------------------------- configuration
 // Tile shapes of the pass kernel: threads x keys-per-thread, and the CTAs/SM the register
-// allocation is bounded for.  One CTA sorts one tile per pass.  Several shapes are compiled in
-// so they can be A/B-measured on the device (VrdxCudaSorterOptions::reserved[0..1] or the
-// VRDX_KEYS_VARIANT / VRDX_KV_VARIANT environment variables pick one at sorter creation);
-// index 0 of each table is the tuned default.
-struct PassVariant {
+// allocation is bounded for.  One CTA sorts one tile per pass.  The product library carries the
+// shapes VRDX_CUDA_ALGORITHM_AUTO can pick plus the few alternates the tuning sweeps compare
+// (VrdxCudaSorterOptions::reserved[0..1], index + 1); every other variant that was measured and
+// lost lives in vrdx_experiments.cuh and is compiled only with -DVRDX_EXPERIMENTS.
+struct TileShape {
   int threads, items, min_ctas;
-  bool tma;     // persistent kernel with cp.async.bulk tile staging (needs 16-byte aligned buffers)
-  int cluster;  // CTAs per thread-block cluster sharing one look-back (0: per-tile look-back)
   uint32_t tile;
   size_t smem;
-  cudaError_t (*prepare)(int* ctas_per_sm);
-  cudaError_t (*launch)(cudaStream_t, uint32_t, const PassArgs&);          // onesweep pass
-  cudaError_t (*launch_downsweep)(cudaStream_t, uint32_t, const PassArgs&);  // reduce-then-scan: scatter pass
-  cudaError_t (*launch_upsweep)(cudaStream_t, uint32_t, const PassArgs&);    // reduce-then-scan: tile histograms
-  cudaError_t (*launch_inorder)(cudaStream_t, uint32_t, const PassArgs&);    // onesweep, tile id = blockIdx.x (experiment)
-  // the same two kernels compiled for an arbitrary digit plan / key codec (vrdxCudaCmdSortEx); only the
-  // default shapes carry them
-  cudaError_t (*launch_generic)(cudaStream_t, uint32_t, const PassArgs&);
-  cudaError_t (*launch_downsweep_generic)(cudaStream_t, uint32_t, const PassArgs&);
+  cudaError_t (*prepare)(int* ctas_per_sm);  // per device: opt every instantiation into its shared-memory size
+  // mode 0: onesweep pass, 1: reduce-then-scan scatter pass; generic: digit plan / key codec from PassArgs
+  cudaError_t (*launch_pass)(cudaStream_t, uint32_t grid, const PassArgs&, int mode, bool generic, bool pdl);
+  cudaError_t (*launch_upsweep)(cudaStream_t, uint32_t grid, const PassArgs&, bool pdl);
 };
 
 // Launch with (or without) the programmatic-dependent-launch attribute; see GridDepWait().
-// Process-wide developer switch (VRDX_PDL=0), read once per sorter creation; not sort state.
-static bool g_pdl = true;
 template <typename... KArgs, typename... Args>
 cudaError_t LaunchEx(void (*kernel)(KArgs...), uint32_t grid, uint32_t block, size_t smem, cudaStream_t stream,
                      bool pdl, Args&&... args) {
@@ -66,173 +57,86 @@ cudaError_t LaunchEx(void (*kernel)(KArgs...), uint32_t grid, uint32_t block, si
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (pdl && g_pdl) ? 1 : 0;
+  cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 template <class Cfg>
-cudaError_t PrepareDirect(int* ctas_per_sm) {
-  cudaError_t e = cudaFuncSetAttribute(OnesweepKernel<Cfg, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)Cfg::kSmemBytes);
+cudaError_t PrepareShape(int* ctas_per_sm) {
+  cudaError_t e = cudaSuccess;
+  auto opt_in = [&](void (*k)(const PassArgs)) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
+  };
+  opt_in(PassKernel<Cfg, 0, false>);
+  opt_in(PassKernel<Cfg, 1, false>);
+  opt_in(PassKernel<Cfg, 0, true>);
+  opt_in(PassKernel<Cfg, 1, true>);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(OnesweepKernel<Cfg, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)Cfg::kSmemBytes);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(OnesweepKernel<Cfg, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)Cfg::kSmemBytes);
-  if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, OnesweepKernel<Cfg, 0>, Cfg::kThreads,
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, PassKernel<Cfg, 1, false>, Cfg::kThreads,
                                                        Cfg::kSmemBytes);
 }
 template <class Cfg>
-cudaError_t PrepareDirectWithGeneric(int* ctas_per_sm) {
-  cudaError_t e = cudaFuncSetAttribute(OnesweepKernel<Cfg, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)Cfg::kSmemBytes);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(OnesweepKernel<Cfg, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)Cfg::kSmemBytes);
-  if (e != cudaSuccess) return e;
-  return PrepareDirect<Cfg>(ctas_per_sm);
+cudaError_t LaunchPass(cudaStream_t stream, uint32_t grid, const PassArgs& args, int mode, bool generic, bool pdl) {
+  void (*k)(const PassArgs) = mode == 0 ? (generic ? PassKernel<Cfg, 0, true> : PassKernel<Cfg, 0, false>)
+                                        : (generic ? PassKernel<Cfg, 1, true> : PassKernel<Cfg, 1, false>);
+  return LaunchEx(k, grid, Cfg::kThreads, Cfg::kSmemBytes, stream, pdl, args);
 }
 template <class Cfg>
-cudaError_t PrepareTma(int* ctas_per_sm) {
-  cudaError_t e = cudaFuncSetAttribute(OnesweepTmaKernel<Cfg, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)Cfg::kSmemBytes);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(OnesweepTmaKernel<Cfg, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)Cfg::kSmemBytes);
-  if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, OnesweepTmaKernel<Cfg, 1>, Cfg::kThreads,
-                                                       Cfg::kSmemBytes);
-}
-template <class Cfg, int MODE>
-cudaError_t LaunchDirect(cudaStream_t stream, uint32_t grid, const PassArgs& args) {
-  return LaunchEx(OnesweepKernel<Cfg, MODE>, grid, Cfg::kThreads, Cfg::kSmemBytes, stream, true, args);
-}
-template <class Cfg, int MODE>
-cudaError_t LaunchDirectGeneric(cudaStream_t stream, uint32_t grid, const PassArgs& args) {
-  return LaunchEx(OnesweepKernel<Cfg, MODE, true>, grid, Cfg::kThreads, Cfg::kSmemBytes, stream, true, args);
-}
-template <class Cfg, int MODE>
-cudaError_t LaunchTma(cudaStream_t stream, uint32_t grid, const PassArgs& args) {
-  return LaunchEx(OnesweepTmaKernel<Cfg, MODE>, grid, Cfg::kThreads, Cfg::kSmemBytes, stream, true, args);
-}
-template <class Cfg>
-cudaError_t LaunchUpsweep(cudaStream_t stream, uint32_t grid, const PassArgs& args) {
+cudaError_t LaunchUpsweep(cudaStream_t stream, uint32_t grid, const PassArgs& args, bool pdl) {
   // the first kernel of a sort (pass 0) is a normal launch: it must wait for the caller's prior work
-  return LaunchEx(UpsweepKernel<Cfg::kTile>, grid, kUpsweepThreads, 0, stream, args.pass != 0, args.indirect,
-                  args.n_or_max, args.shift, args.mask, args.codec_in, args.keys_in, args.status, args.status_next,
-                  args.hdr, args.ts_end);
+  return LaunchEx(UpsweepKernel<Cfg::kTile, true>, grid, kUpsweepThreads, 0, stream, pdl && args.pass != 0,
+                  args.indirect, args.n_or_max, args.shift, args.mask, args.codec_in, args.keys_in, args.status,
+                  args.status_next, args.hdr, args.ts_end);
 }
-template <int T, int I, bool KV, int M, int LB = 4, bool PAIRED = false>
-constexpr PassVariant MakeVariant() {
-  using Cfg = PassConfig<T, I, KV, M, LB, PAIRED>;
-  return PassVariant{T, I, M, false, 0, (uint32_t)Cfg::kTile, Cfg::kSmemBytes, &PrepareDirect<Cfg>,
-                     &LaunchDirect<Cfg, 0>, &LaunchDirect<Cfg, 1>, &LaunchUpsweep<Cfg>, &LaunchDirect<Cfg, 2>,
-                     nullptr, nullptr};
-}
-// A default shape: also compiled for arbitrary digit plans and key codecs.
 template <int T, int I, bool KV, int M>
-constexpr PassVariant MakeDefaultVariant() {
-  using Cfg = PassConfig<T, I, KV, M, 4, false>;
-  return PassVariant{T, I, M, false, 0, (uint32_t)Cfg::kTile, Cfg::kSmemBytes, &PrepareDirectWithGeneric<Cfg>,
-                     &LaunchDirect<Cfg, 0>, &LaunchDirect<Cfg, 1>, &LaunchUpsweep<Cfg>, &LaunchDirect<Cfg, 2>,
-                     &LaunchDirectGeneric<Cfg, 0>, &LaunchDirectGeneric<Cfg, 1>};
-}
-template <class Cfg, int C>
-cudaError_t PrepareCluster(int* ctas_per_sm) {
-  cudaError_t e = cudaFuncSetAttribute(OnesweepClusterKernel<Cfg, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)Cfg::kSmemBytes);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(OnesweepKernel<Cfg, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
-  if (e != cudaSuccess) return e;
-  *ctas_per_sm = Cfg::kMinCtas;
-  return cudaSuccess;
-}
-template <class Cfg, int C>
-cudaError_t LaunchCluster(cudaStream_t stream, uint32_t grid, const PassArgs& args) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);  // a multiple of C
-  cfg.blockDim = dim3(Cfg::kThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = C;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = g_pdl ? 2 : 1;
-  return cudaLaunchKernelEx(&cfg, OnesweepClusterKernel<Cfg, C>, args);
-}
-template <int T, int I, bool KV, int M, int C, int LB = 4>
-constexpr PassVariant MakeClusterVariant() {
-  using Cfg = PassConfig<T, I, KV, M, LB>;
-  return PassVariant{T, I, M, false, C, (uint32_t)Cfg::kTile, Cfg::kSmemBytes, &PrepareCluster<Cfg, C>,
-                     &LaunchCluster<Cfg, C>, &LaunchDirect<Cfg, 1>, &LaunchUpsweep<Cfg>, nullptr, nullptr, nullptr};
-}
-template <int T, int I, bool KV, int M, int LB = 4>
-constexpr PassVariant MakeTmaVariant() {
-  using Cfg = TmaPassConfig<T, I, KV, M, LB>;
-  return PassVariant{T, I, M, true, 0, (uint32_t)Cfg::kTile, Cfg::kSmemBytes, &PrepareTma<Cfg>, &LaunchTma<Cfg, 0>,
-                     &LaunchTma<Cfg, 1>, &LaunchUpsweep<Cfg>, nullptr, nullptr, nullptr};
+constexpr TileShape MakeShape() {
+  using Cfg = PassConfig<T, I, KV, M>;
+  return TileShape{T, I, M, (uint32_t)Cfg::kTile, Cfg::kSmemBytes, &PrepareShape<Cfg>, &LaunchPass<Cfg>,
+                   &LaunchUpsweep<Cfg>};
 }
 
-// Direct-load variants (one tile per CTA).  Defaults (measured on B200, profiles/):
-//   onesweep, keys and pairs      index 0  384 x 16, 3 CTAs/SM
-//   reduce-then-scan, keys        index 1  256 x 16, 5 CTAs/SM   (no look-back state in registers)
-//   reduce-then-scan, pairs       index 0
-// The rest are kept selectable for A/B runs (VrdxCudaSorterOptions::reserved / VRDX_*_VARIANT) and
-// are exercised by the test-suite where they change the algorithm (cluster look-back, paired staging).
-static const PassVariant kKeysVariants[] = {
-    MakeDefaultVariant<384, 16, false, 3>(),    MakeDefaultVariant<256, 16, false, 5>(),
-    MakeVariant<512, 16, false, 2>(),           MakeVariant<256, 16, false, 4>(),
-    MakeVariant<384, 12, false, 4>(),           MakeClusterVariant<384, 16, false, 3, 4>(),
-    MakeClusterVariant<384, 16, false, 3, 8>(), MakeVariant<384, 16, false, 3, 16>(),
-    MakeVariant<384, 16, false, 3>(),  // placeholder so keys and pairs tables index alike
+// Shapes (measured on B200, profiles/r02_shape_sweep.txt).  Index 0 is the onesweep default,
+// kDefault*RtsShape the reduce-then-scan default.
+static const TileShape kKeysShapes[] = {
+    MakeShape<384, 16, false, 3>(), MakeShape<256, 16, false, 5>(), MakeShape<256, 16, false, 4>(),
+    MakeShape<256, 16, false, 6>(), MakeShape<512, 16, false, 2>(),
 };
-static const PassVariant kPairVariants[] = {
-    MakeDefaultVariant<384, 16, true, 3>(),     MakeVariant<256, 16, true, 5>(),
-    MakeVariant<512, 16, true, 2>(),            MakeVariant<256, 16, true, 4>(),
-    MakeVariant<384, 12, true, 4>(),            MakeClusterVariant<384, 16, true, 3, 4>(),
-    MakeClusterVariant<384, 16, true, 3, 8>(),  MakeVariant<384, 16, true, 3, 16>(),
-    MakeVariant<384, 16, true, 3, 4, true>(),  // (key, value) staged as one 64-bit element: measured slower
+static const TileShape kPairShapes[] = {
+    MakeShape<384, 16, true, 3>(), MakeShape<256, 16, true, 5>(), MakeShape<256, 16, true, 4>(),
+    MakeShape<256, 16, true, 3>(), MakeShape<512, 16, true, 2>(),
 };
-constexpr int kDefaultKeysRtsVariant = 1;
-constexpr int kDefaultPairRtsVariant = 0;
-constexpr int kDefaultOnesweepVariant = 0;  // keys and pairs
-// Persistent TMA-staged variants (selected only with VRDX_CUDA_TILE_LOAD_TMA; measured slower than
-// the direct kernels on B200).
-static const PassVariant kKeysTmaVariants[] = {
-    MakeTmaVariant<256, 16, false, 4>(), MakeTmaVariant<384, 16, false, 3>(), MakeTmaVariant<512, 16, false, 2>(),
-};
-static const PassVariant kPairTmaVariants[] = {
-    MakeTmaVariant<384, 20, true, 2>(), MakeTmaVariant<384, 16, true, 2>(), MakeTmaVariant<512, 16, true, 2>(),
-};
-constexpr int kNumKeysVariants = sizeof(kKeysVariants) / sizeof(kKeysVariants[0]);
-constexpr int kNumPairVariants = sizeof(kPairVariants) / sizeof(kPairVariants[0]);
-constexpr int kNumKeysTmaVariants = sizeof(kKeysTmaVariants) / sizeof(kKeysTmaVariants[0]);
-constexpr int kNumPairTmaVariants = sizeof(kPairTmaVariants) / sizeof(kPairTmaVariants[0]);
-// Smallest tile of any compiled variant: sizes the look-back buffers whichever variant runs.
+constexpr int kDefaultKeysRtsShape = 1;
+constexpr int kDefaultPairRtsShape = 0;
+constexpr int kDefaultOnesweepShape = 0;  // keys and pairs
+constexpr int kNumKeysShapes = sizeof(kKeysShapes) / sizeof(kKeysShapes[0]);
+constexpr int kNumPairShapes = sizeof(kPairShapes) / sizeof(kPairShapes[0]);
+// Smallest tile of any compiled shape: sizes the per-tile tables whichever shape runs.
 constexpr uint32_t kMinTile = 4096;  // 256 x 16
 // AUTO: reduce-then-scan at and above this count, onesweep (fewer launches) below it.
-// the conflict-free histogram kernel needs enough keys to fill one 1024-thread CTA per SM
-static uint32_t g_hist_private_min_count = 1u << 21;  // developer override: VRDX_HIST_PRIVATE_MIN
 constexpr uint32_t kAutoRtsThresholdKeys = 3u << 23;   // measured crossovers (profiles/r01_sweep_n_final.txt):
 constexpr uint32_t kAutoRtsThresholdPairs = 3u << 24;  // keys-only ~2^24.6, key-value ~2^25.6
+// the conflict-free histogram kernel needs enough keys to fill one 1024-thread CTA per SM
+constexpr uint32_t kHistPrivateMinCount = 1u << 21;
 
+#ifdef VRDX_EXPERIMENTS
+#include "vrdx_experiments_host.inc"
+#endif
+
+// Immutable after creation (threading row): every per-sort decision reads these fields
+// or the arguments of the call; there is no process-wide state in the library.
 struct VrdxSorter_T {
   int device = 0;
   int sm_count = 0;
   int cc_major = 0, cc_minor = 0;
   VrdxCudaAlgorithm algorithm = VRDX_CUDA_ALGORITHM_AUTO;
   VrdxCudaTileLoad tile_load = VRDX_CUDA_TILE_LOAD_AUTO;
-  int keys_variant = 0, pair_variant = 0;          // direct-load kernels, onesweep
-  int keys_rts_variant = kDefaultKeysRtsVariant, pair_rts_variant = kDefaultPairRtsVariant;  // reduce-then-scan
-  int keys_tma_variant = 0, pair_tma_variant = 0;  // persistent TMA kernels
-  int keys_ctas = 1, pair_ctas = 1, keys_tma_ctas = 1, pair_tma_ctas = 1;  // co-resident CTAs per SM
+  int keys_shape = kDefaultOnesweepShape, pair_shape = kDefaultOnesweepShape;        // onesweep
+  int keys_rts_shape = kDefaultKeysRtsShape, pair_rts_shape = kDefaultPairRtsShape;  // reduce-then-scan
+  bool pdl = true;                                        // programmatic dependent launch between our own kernels
+  uint32_t hist_private_min_count = kHistPrivateMinCount;  // lane-private histogram bins from this count up
+#ifdef VRDX_EXPERIMENTS
+  ExperimentSelection exp;
+#endif
   // The only mutable words: a sticky error and a launch counter (diagnostics, not sort state).
   std::atomic<int> last_error{0};
   std::atomic<uint32_t> last_launches{0};
@@ -404,28 +308,29 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
   uint32_t* keys_alt = reinterpret_cast<uint32_t*>(storage + lay.keys_alt_offset);
   uint32_t* vals_alt = reinterpret_cast<uint32_t*>(storage + lay.values_alt_offset);
 
-  // TMA staging needs 16-byte aligned sources in both ping-pong directions.
-  auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-  const bool can_tma = aligned16(keys) && aligned16(storage) && (!kv || aligned16(values));
-  // Key types, order and bit sub-ranges are implemented by the direct-load tile kernel; the
-  // experimental flavours (persistent TMA staging, cluster look-back) only know the reference's plan.
-  // Only the default shapes are compiled for them, so such a sort ignores the sorter's A/B selectors.
-  const bool generic = !plan.reference;
-  const bool use_tma = sorter->tile_load == VRDX_CUDA_TILE_LOAD_TMA && can_tma && !generic;
-  const PassVariant& variant =
-      generic ? (use_rts ? (kv ? kPairVariants[kDefaultPairRtsVariant] : kKeysVariants[kDefaultKeysRtsVariant])
-                         : (kv ? kPairVariants[kDefaultOnesweepVariant] : kKeysVariants[kDefaultOnesweepVariant]))
-      : use_tma ? (kv ? kPairTmaVariants[sorter->pair_tma_variant] : kKeysTmaVariants[sorter->keys_tma_variant])
-      : use_rts ? (kv ? kPairVariants[sorter->pair_rts_variant] : kKeysVariants[sorter->keys_rts_variant])
-                : (kv ? kPairVariants[sorter->pair_variant] : kKeysVariants[sorter->keys_variant]);
-  const uint32_t tiles = (uint32_t)CeilDiv(n_or_max, variant.tile);
-  uint32_t pass_grid = tiles;
-  if (!use_rts && !use_tma && variant.cluster > 1)  // whole clusters; CTAs past the count only serve their digit slice
-    pass_grid = (uint32_t)CeilDiv(tiles, (uint64_t)variant.cluster) * (uint32_t)variant.cluster;
-  if (use_tma) {  // persistent: one wave of co-resident CTAs
-    const uint32_t wave = (uint32_t)sorter->sm_count * (uint32_t)(kv ? sorter->pair_tma_ctas : sorter->keys_tma_ctas);
-    pass_grid = tiles < wave ? tiles : wave;
+  // Alignment: the header and tables are accessed as 16-byte vectors, keys/values as words.
+  if ((reinterpret_cast<uintptr_t>(storage) & (kOffsetAlignment - 1)) || (reinterpret_cast<uintptr_t>(keys) & 3u) ||
+      (kv && (reinterpret_cast<uintptr_t>(values) & 3u)) || (reinterpret_cast<uintptr_t>(indirect) & 3u)) {
+    NoteError(sorter, cudaErrorInvalidValue);
+    for (int i = 1; i < 15; ++i) st.Same(i);
+    sorter->last_launches.store(0);
+    return;
   }
+  // Key types, order and bit sub-ranges run the GENERIC instantiation of the same tile kernel.
+  const bool generic = !plan.reference;
+  const bool pdl = sorter->pdl;
+  const TileShape& shape = use_rts ? (kv ? kPairShapes[sorter->pair_rts_shape] : kKeysShapes[sorter->keys_rts_shape])
+                                   : (kv ? kPairShapes[sorter->pair_shape] : kKeysShapes[sorter->keys_shape]);
+  uint32_t tile_size = shape.tile;
+#ifdef VRDX_EXPERIMENTS
+  const ExperimentKernel* ek = generic ? nullptr : PickExperiment(sorter->exp, kv, keys, values, storage);
+  if (ek) tile_size = ek->tile;
+#endif
+  const uint32_t tiles = (uint32_t)CeilDiv(n_or_max, tile_size);
+  uint32_t pass_grid = tiles;
+#ifdef VRDX_EXPERIMENTS
+  if (ek) pass_grid = ExperimentGrid(*ek, tiles, use_rts, sorter->sm_count);
+#endif
 
   if (!use_rts) {
     // Reset per-sort state inside the stream (reference: vkCmdFillBuffer of the global
@@ -434,7 +339,7 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
                                       lay.status_a_offset + (uint64_t)tiles * kRadix * sizeof(uint32_t),
                                       stream));
     ++launches;
-    if (n_or_max >= g_hist_private_min_count) {
+    if (n_or_max >= sorter->hist_private_min_count) {
       // lane-private (conflict-free) bins, one 1024-thread CTA per SM
       uint64_t chunks = CeilDiv(n_or_max, (uint64_t)kHistPrivChunk);
       uint32_t grid = (uint32_t)(chunks < (uint64_t)sorter->sm_count ? chunks : (uint64_t)sorter->sm_count);
@@ -473,24 +378,32 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
     args.vals_out = kv ? ((pass & 1) ? values : vals_alt) : nullptr;
 
     if (use_rts) {
-      // the reference's three stages: status A = [tile][256] histograms -> exclusive prefixes,
-      // status B = spine chunk sums; timestamps fall exactly where the reference puts them
+      // the reference's three stages: status A = per-tile digit prefixes inside a chunk of kSpineChunk
+      // tiles, status B = spine chunk sums -> exclusive prefixes; timestamps fall exactly where the
+      // reference puts them
       args.status = status[0];
       args.status_next = status[1];
       const uint32_t chunks = (uint32_t)CeilDiv(tiles, (uint64_t)kSpineChunk);
       args.ts_end = st.Written(2 + 3 * pass + 0);
-      NoteError(sorter, variant.launch_upsweep(stream, chunks, args));
+#ifdef VRDX_EXPERIMENTS
+      if (ek) NoteError(sorter, ek->launch_upsweep(stream, chunks, args, pdl));
+      else
+#endif
+      NoteError(sorter, shape.launch_upsweep(stream, chunks, args, pdl));
       // spine scratch: chunk prefixes occupy rows [0, chunks) of status B, segment sums the rows after them
       uint32_t* seg = status[1] + (size_t)chunks * kRadix;
       const uint32_t seg_grid = chunks < (uint32_t)kSpineSegments ? (chunks ? chunks : 1u) : (uint32_t)kSpineSegments;
-      NoteError(sorter, LaunchEx(SpineReduceKernel, seg_grid, (uint32_t)kRadix, 0, stream, true, indirect,
-                                 n_or_max, variant.tile, pass, (const uint32_t*)status[1], seg, hdr));
-      NoteError(sorter, LaunchEx(SpineApplyKernel, seg_grid, (uint32_t)kRadix, 0, stream, true, indirect,
-                                 n_or_max, variant.tile, status[1], (const uint32_t*)seg,
+      NoteError(sorter, LaunchEx(SpineReduceKernel, seg_grid, (uint32_t)kRadix, 0, stream, pdl, indirect,
+                                 n_or_max, tile_size, pass, (const uint32_t*)status[1], seg, hdr));
+      NoteError(sorter, LaunchEx(SpineApplyKernel, seg_grid, (uint32_t)kRadix, 0, stream, pdl, indirect,
+                                 n_or_max, tile_size, status[1], (const uint32_t*)seg,
                                  st.Written(2 + 3 * pass + 1)));
       args.ts_end = st.Written(2 + 3 * pass + 2);
-      NoteError(sorter, generic ? variant.launch_downsweep_generic(stream, tiles, args)
-                                : variant.launch_downsweep(stream, use_tma ? pass_grid : tiles, args));
+#ifdef VRDX_EXPERIMENTS
+      if (ek) NoteError(sorter, ek->launch(stream, pass_grid, args, 1, pdl));
+      else
+#endif
+      NoteError(sorter, shape.launch_pass(stream, tiles, args, 1, generic, pdl));
       launches += 4;
       continue;
     }
@@ -498,10 +411,11 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
     st.Same(2 + 3 * pass + 0);
     st.Same(2 + 3 * pass + 1);
     args.ts_end = st.Written(2 + 3 * pass + 2);
-    static const bool inorder = getenv("VRDX_TILE_ORDER") && atoi(getenv("VRDX_TILE_ORDER")) == 1;
-    NoteError(sorter, generic                               ? variant.launch_generic(stream, pass_grid, args)
-                      : (inorder && variant.launch_inorder) ? variant.launch_inorder(stream, pass_grid, args)
-                                                            : variant.launch(stream, pass_grid, args));
+#ifdef VRDX_EXPERIMENTS
+    if (ek) NoteError(sorter, ek->launch(stream, pass_grid, args, 0, pdl));
+    else
+#endif
+    NoteError(sorter, shape.launch_pass(stream, pass_grid, args, 0, generic, pdl));
     ++launches;
   }
   for (uint32_t pass = passes; pass < (uint32_t)kPasses; ++pass)  // passes a bit sub-range does not need
@@ -510,7 +424,7 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
     // an odd number of passes ends in the scratch halves: bring [0, count) home
     const uint64_t blocks = CeilDiv((uint64_t)n_or_max, (uint64_t)1024);
     const uint64_t cap = (uint64_t)sorter->sm_count * 8;
-    NoteError(sorter, LaunchEx(CopyBackKernel, (uint32_t)(blocks < cap ? blocks : cap), 256u, 0, stream, true, indirect,
+    NoteError(sorter, LaunchEx(CopyBackKernel, (uint32_t)(blocks < cap ? blocks : cap), 256u, 0, stream, pdl, indirect,
                                n_or_max, (const uint32_t*)keys_alt, keys, kv ? (const uint32_t*)vals_alt : nullptr,
                                kv ? values : nullptr, st.Written(14)));
     ++launches;
@@ -544,46 +458,48 @@ VkResult vrdxCudaCreateSorter(const VrdxSorterCreateInfo* pCreateInfo,
   if (prop.major != 10) return VK_ERROR_FEATURE_NOT_PRESENT;  // kernels are built for sm_100a only
 
   DeviceGuard guard(dev);
-  int keys_variant = 0, pair_variant = 0, keys_tma_variant = 0, pair_tma_variant = 0;
+  // Developer overrides (environment) are read ONCE, here, into the sorter; nothing on the sort path
+  // reads the environment or any process-wide variable.
+  int keys_shape = kDefaultOnesweepShape, pair_shape = kDefaultOnesweepShape;
+  int keys_rts_shape = kDefaultKeysRtsShape, pair_rts_shape = kDefaultPairRtsShape;
+  uint32_t experiment = 0;
   VrdxCudaTileLoad tile_load = VRDX_CUDA_TILE_LOAD_AUTO;
-  if (const char* e = getenv("VRDX_KEYS_VARIANT")) keys_variant = atoi(e);
-  if (const char* e = getenv("VRDX_KV_VARIANT")) pair_variant = atoi(e);
-  int keys_rts_variant = kDefaultKeysRtsVariant, pair_rts_variant = kDefaultPairRtsVariant;
-  if (const char* e = getenv("VRDX_KEYS_RTS_VARIANT")) keys_rts_variant = atoi(e);
-  if (const char* e = getenv("VRDX_KV_RTS_VARIANT")) pair_rts_variant = atoi(e);
-  if (const char* e = getenv("VRDX_KEYS_TMA_VARIANT")) keys_tma_variant = atoi(e);
-  if (const char* e = getenv("VRDX_KV_TMA_VARIANT")) pair_tma_variant = atoi(e);
+  if (const char* e = getenv("VRDX_KEYS_SHAPE")) keys_shape = atoi(e);
+  if (const char* e = getenv("VRDX_KV_SHAPE")) pair_shape = atoi(e);
+  if (const char* e = getenv("VRDX_KEYS_RTS_SHAPE")) keys_rts_shape = atoi(e);
+  if (const char* e = getenv("VRDX_KV_RTS_SHAPE")) pair_rts_shape = atoi(e);
+  if (const char* e = getenv("VRDX_EXPERIMENT")) experiment = (uint32_t)atoi(e);
   if (const char* e = getenv("VRDX_TILE_LOAD")) tile_load = (VrdxCudaTileLoad)atoi(e);
   if (pOptions && pOptions->structSize >= sizeof(VrdxCudaSorterOptions)) {
     if (pOptions->tileLoad != VRDX_CUDA_TILE_LOAD_AUTO) tile_load = pOptions->tileLoad;
-    if (pOptions->reserved[0]) keys_variant = (int)pOptions->reserved[0] - 1;
-    if (pOptions->reserved[1]) pair_variant = (int)pOptions->reserved[1] - 1;
-    if (pOptions->reserved[2]) keys_tma_variant = (int)pOptions->reserved[2] - 1;
-    if (pOptions->reserved[3]) pair_tma_variant = (int)pOptions->reserved[3] - 1;
-    if (pOptions->reserved[4]) keys_rts_variant = pair_rts_variant = (int)pOptions->reserved[4] - 1;
+    if (pOptions->reserved[0]) keys_shape = keys_rts_shape = (int)pOptions->reserved[0] - 1;
+    if (pOptions->reserved[1]) pair_shape = pair_rts_shape = (int)pOptions->reserved[1] - 1;
+    if (pOptions->reserved[2]) experiment = pOptions->reserved[2];
   }
-  if (keys_variant < 0 || keys_variant >= kNumKeysVariants || pair_variant < 0 || pair_variant >= kNumPairVariants ||
-      keys_rts_variant < 0 || keys_rts_variant >= kNumKeysVariants || pair_rts_variant < 0 ||
-      pair_rts_variant >= kNumPairVariants || kKeysVariants[keys_rts_variant].cluster > 1 ||
-      kPairVariants[pair_rts_variant].cluster > 1 ||
-      keys_tma_variant < 0 || keys_tma_variant >= kNumKeysTmaVariants || pair_tma_variant < 0 ||
-      pair_tma_variant >= kNumPairTmaVariants)
+  if (keys_shape < 0 || keys_shape >= kNumKeysShapes || pair_shape < 0 || pair_shape >= kNumPairShapes ||
+      keys_rts_shape < 0 || keys_rts_shape >= kNumKeysShapes || pair_rts_shape < 0 || pair_rts_shape >= kNumPairShapes)
     return VK_ERROR_INITIALIZATION_FAILED;
-  // "Pipeline creation": opt the pass kernels into their shared-memory footprint and ask how many
-  // CTAs of each are co-resident per SM (the persistent kernels launch exactly one such wave).
-  int keys_ctas = 1, pair_ctas = 1, keys_tma_ctas = 1, pair_tma_ctas = 1;
+#ifndef VRDX_EXPERIMENTS
+  // the TMA-staged persistent kernels and the other losing variants are not in the product library
+  if (experiment != 0 || tile_load == VRDX_CUDA_TILE_LOAD_TMA) return VK_ERROR_FEATURE_NOT_PRESENT;
+#endif
+  // "Pipeline creation" (h.in:141-262): opt every kernel this sorter can launch into its shared-memory
+  // footprint.  cudaFuncSetAttribute applies to the CURRENT device, so this runs for every sorter, under
+  // the device guard above: a process that drives several GPUs prepares each of them.
   int unused = 0;
-  if (kKeysVariants[kDefaultOnesweepVariant].prepare(&unused) != cudaSuccess ||  // vrdxCudaCmdSortEx runs the defaults
-      kPairVariants[kDefaultOnesweepVariant].prepare(&unused) != cudaSuccess ||
-      kKeysVariants[kDefaultKeysRtsVariant].prepare(&unused) != cudaSuccess ||
-      kPairVariants[kDefaultPairRtsVariant].prepare(&unused) != cudaSuccess ||
-      kKeysVariants[keys_rts_variant].prepare(&unused) != cudaSuccess ||
-      kPairVariants[pair_rts_variant].prepare(&unused) != cudaSuccess ||
-      kKeysVariants[keys_variant].prepare(&keys_ctas) != cudaSuccess ||
-      kPairVariants[pair_variant].prepare(&pair_ctas) != cudaSuccess ||
-      kKeysTmaVariants[keys_tma_variant].prepare(&keys_tma_ctas) != cudaSuccess ||
-      kPairTmaVariants[pair_tma_variant].prepare(&pair_tma_ctas) != cudaSuccess || keys_tma_ctas < 1 ||
-      pair_tma_ctas < 1) {
+  if (kKeysShapes[kDefaultOnesweepShape].prepare(&unused) != cudaSuccess ||  // vrdxCudaCmdSortEx runs the defaults too
+      kPairShapes[kDefaultOnesweepShape].prepare(&unused) != cudaSuccess ||
+      kKeysShapes[kDefaultKeysRtsShape].prepare(&unused) != cudaSuccess ||
+      kPairShapes[kDefaultPairRtsShape].prepare(&unused) != cudaSuccess ||
+      kKeysShapes[keys_shape].prepare(&unused) != cudaSuccess || kPairShapes[pair_shape].prepare(&unused) != cudaSuccess ||
+      kKeysShapes[keys_rts_shape].prepare(&unused) != cudaSuccess ||
+      kPairShapes[pair_rts_shape].prepare(&unused) != cudaSuccess ||
+      cudaFuncSetAttribute(HistogramKernelPrivate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)kHistPrivSmemBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(HistogramKernelPrivate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)kHistPrivSmemBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(DistPrefixHistogramKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)kDistHistMaxSmemBytes) != cudaSuccess) {
     cudaGetLastError();
     return VK_ERROR_INITIALIZATION_FAILED;
   }
@@ -593,28 +509,21 @@ VkResult vrdxCudaCreateSorter(const VrdxSorterCreateInfo* pCreateInfo,
   s->sm_count = prop.multiProcessorCount;
   s->cc_major = prop.major;
   s->cc_minor = prop.minor;
-  s->keys_variant = keys_variant;
-  s->pair_variant = pair_variant;
-  s->keys_rts_variant = keys_rts_variant;
-  s->pair_rts_variant = pair_rts_variant;
-  s->keys_tma_variant = keys_tma_variant;
-  s->pair_tma_variant = pair_tma_variant;
-  s->keys_ctas = keys_ctas;
-  s->pair_ctas = pair_ctas;
-  s->keys_tma_ctas = keys_tma_ctas;
-  s->pair_tma_ctas = pair_tma_ctas;
+  s->keys_shape = keys_shape;
+  s->pair_shape = pair_shape;
+  s->keys_rts_shape = keys_rts_shape;
+  s->pair_rts_shape = pair_rts_shape;
   s->tile_load = tile_load;
   if (const char* e = getenv("VRDX_ALGORITHM")) s->algorithm = (VrdxCudaAlgorithm)atoi(e);
-  if (const char* e = getenv("VRDX_PDL")) g_pdl = atoi(e) != 0;
-  if (const char* e = getenv("VRDX_HIST_PRIVATE_MIN")) g_hist_private_min_count = (uint32_t)strtoul(e, nullptr, 10);
-  if (cudaFuncSetAttribute(HistogramKernelPrivate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)kHistPrivSmemBytes) != cudaSuccess ||
-      cudaFuncSetAttribute(HistogramKernelPrivate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)kHistPrivSmemBytes) != cudaSuccess) {
+  if (const char* e = getenv("VRDX_PDL")) s->pdl = atoi(e) != 0;
+  if (const char* e = getenv("VRDX_HIST_PRIVATE_MIN")) s->hist_private_min_count = (uint32_t)strtoul(e, nullptr, 10);
+#ifdef VRDX_EXPERIMENTS
+  if (!PrepareExperiments(&s->exp, experiment, tile_load, s->sm_count)) {
     cudaGetLastError();
     delete s;
     return VK_ERROR_INITIALIZATION_FAILED;
   }
+#endif
   if (pOptions && pOptions->structSize >= sizeof(VrdxCudaSorterOptions) &&
       pOptions->algorithm != VRDX_CUDA_ALGORITHM_AUTO)
     s->algorithm = pOptions->algorithm;
@@ -868,7 +777,7 @@ void vrdxCudaCmdSortKeys64(VkCommandBuffer commandBuffer, VrdxSorter sorter, con
     sorter->last_launches.store(0);
     return;
   }
-  if (!keys || !storage || (reinterpret_cast<uintptr_t>(keys) & 7u) || (reinterpret_cast<uintptr_t>(storage) & 3u)) {
+  if (!keys || !storage || (reinterpret_cast<uintptr_t>(keys) & 7u) || (reinterpret_cast<uintptr_t>(storage) & (kOffsetAlignment - 1))) {
     NoteError(sorter, cudaErrorInvalidValue);
     return;
   }
@@ -978,9 +887,8 @@ void vrdxCudaGetSorterProperties(VrdxSorter sorter, VrdxCudaSorterProperties* p)
   p->smCount = sorter->sm_count;
   p->ccMajor = sorter->cc_major;
   p->ccMinor = sorter->cc_minor;
-  const bool tma = sorter->tile_load == VRDX_CUDA_TILE_LOAD_TMA;
-  p->keysTileSize = tma ? kKeysTmaVariants[sorter->keys_tma_variant].tile : kKeysVariants[sorter->keys_variant].tile;
-  p->keyValueTileSize = tma ? kPairTmaVariants[sorter->pair_tma_variant].tile : kPairVariants[sorter->pair_variant].tile;
+  p->keysTileSize = kKeysShapes[sorter->keys_shape].tile;
+  p->keyValueTileSize = kPairShapes[sorter->pair_shape].tile;
   p->offsetAlignment = kOffsetAlignment;
   p->maxOnesweepCount = (uint32_t)kMaxOnesweepCount;
 }
@@ -994,7 +902,7 @@ void vrdxDistCmdPrefixHistogram(VkCommandBuffer commandBuffer, VrdxSorter sorter
   if (!sorter) return;
   const size_t smem = (size_t)prefixCount * ((size_t)1 << (digitBits & 31)) * sizeof(uint32_t);
   if (!keysBuffer || !histogramBuffer || prefixCount == 0 || prefixCount > (uint32_t)kDistMaxSplitters ||
-      digitBits == 0 || digitBits > 12 || shift + digitBits > 32 || smem > 160 * 1024 ||
+      digitBits == 0 || digitBits > 12 || shift + digitBits > 32 || smem > kDistHistMaxSmemBytes ||
       (!prefixesBuffer && shift + digitBits < 32)) {
     NoteError(sorter, cudaErrorInvalidValue);
     return;
@@ -1007,10 +915,7 @@ void vrdxDistCmdPrefixHistogram(VkCommandBuffer commandBuffer, VrdxSorter sorter
       prefixesBuffer ? reinterpret_cast<const uint32_t*>(reinterpret_cast<char*>(prefixesBuffer) + prefixesOffset)
                      : reinterpret_cast<const uint32_t*>(keys);  // never read when the prefix is empty
   uint32_t* hist = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(histogramBuffer) + histogramOffset);
-  static std::atomic<bool> prepared{false};
-  if (!prepared.exchange(true))
-    NoteError(sorter, cudaFuncSetAttribute(DistPrefixHistogramKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           160 * 1024));
+  // (the kernel was opted into kDistHistMaxSmemBytes of dynamic shared memory on this device by vrdxCudaCreateSorter)
   const uint64_t vec_blocks = CeilDiv((uint64_t)elementCount / 4 + 1, (uint64_t)kDistHistThreads);
   const uint64_t cap = (uint64_t)sorter->sm_count * (smem > 112 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4));
   const uint32_t grid = (uint32_t)(vec_blocks < cap ? vec_blocks : cap);

@@ -21,6 +21,7 @@ struct DistPrefixes {
 // Algorithmic traffic 4 B/key.  Grid-stride, 128-bit loads, shared-memory histograms
 // (prefixCount x 256 bins), one global atomic per non-empty bin at the end.
 constexpr int kDistHistThreads = 512;
+constexpr size_t kDistHistMaxSmemBytes = 160 * 1024;  // dynamic shared memory the kernel is opted into per device (vrdxCudaCreateSorter)
 
 __global__ void __launch_bounds__(kDistHistThreads)
 DistPrefixHistogramKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t shift, uint32_t digit_bits,

@@ -385,41 +385,8 @@ struct PassConfig {
   static constexpr size_t kSmemBytes =
       sizeof(uint32_t) * ((size_t)kWarps * kRadix + (size_t)kTile * (KV ? 2 : 1) + kRadix + kMiscWords);
   static_assert(THREADS % 32 == 0 && THREADS >= kRadix && THREADS <= 1024, "one thread per digit is assumed");
-  static_assert(kTile <= (1 << 16), "tile ranks are kept below 2^16");
+  static_assert(kTile <= (1 << 14), "byte offsets of tile slots are kept below 2^16");
 };
-
-// Rank of one key among the keys of its warp that hold the same digit and come earlier in
-// (item, lane) order; `cnt` is the warp-private counter row.  See the block comment above.
-__device__ __forceinline__ uint32_t WarpRankDigit(uint32_t* cnt, uint32_t d, uint32_t lt) {
-  const uint32_t old = atomicAdd(&cnt[d], 1u);   // optimistic: exact if no other lane holds digit d
-  __syncwarp();
-  const uint32_t fin = cnt[d];                   // all 32 increments of this item have landed
-  uint32_t r = old;
-  uint32_t suspects = __ballot_sync(0xffffffffu, fin - old > 1u);  // someone was served after me
-  if (suspects != 0u) {                                            // warp-uniform
-    if (__popc(suspects) > kRepairBallotThreshold) {
-      // many collisions (low-entropy digit): fixed-cost peer masks for every lane
-      uint32_t peers = 0xffffffffu;
-#pragma unroll
-      for (int b = 0; b < kRadixBits; ++b) {
-        const bool bit = (d >> b) & 1u;
-        const uint32_t m = __ballot_sync(0xffffffffu, bit);
-        peers &= bit ? m : ~m;
-      }
-      r = fin - __popc(peers) + __popc(peers & lt);
-    } else {
-      // few collision groups: repair them one by one, in lane order
-      do {
-        const uint32_t dstar = __shfl_sync(0xffffffffu, d, __ffs(suspects) - 1);
-        const uint32_t peers = __ballot_sync(0xffffffffu, d == dstar);
-        if (d == dstar) r = fin - __popc(peers) + __popc(peers & lt);
-        suspects &= ~peers;
-      } while (suspects != 0u);
-    }
-  }
-  __syncwarp();
-  return r;
-}
 
 // Decoupled look-back for one digit: exclusive prefix over tiles [0, tile).  kLookBatch cells are
 // in flight per round trip; `look_s` holds the first batch (tiles tile-1 .. tile-kLookBatch),
@@ -491,26 +458,125 @@ __device__ __forceinline__ uint32_t LookBack(const uint32_t* status, uint32_t ti
   return excl;
 }
 
-// MODE 0: onesweep (tile ids from the ticket counter, offsets by decoupled look-back).
-// MODE 2: onesweep with tile id = blockIdx.x (no ticket): relies on CTAs being dispatched in
-//         increasing blockIdx order, as CUB's decoupled-look-back DeviceScan does.
-// MODE 1: downsweep of the reduce-then-scan variant — tile id = blockIdx.x and `a.status` already
-//         holds the exclusive prefix over tiles of every digit (UpsweepKernel + Spine*Kernel), so
-//         the kernel has no inter-CTA communication at all (the reference's downsweep shape).
-// GENERIC = false: the reference's plan (shift = 8 * pass, mask = 0xFF, no codec) folded at compile
-// time — the code the measurements in DESIGN.md are about.  GENERIC = true: digit and codec from PassArgs.
-template <class Cfg, int MODE = 0, bool GENERIC = false>
+// ------------------------------------------------------------------------------------------
+// PassKernel — the tile kernel of round 2: the same algorithm as OnesweepKernel (one LSD pass over
+// one tile per CTA: load, warp-level multi-split ranking, per-digit scan, tile-local reorder
+// through shared memory, run-wise coalesced scatter), rewritten around what the ncu source view
+// of OnesweepKernel showed (profiles/r02_*): 78 warp-instructions and 20.5 shared-memory
+// wavefronts per 32 keys, the instruction count being the first limiter.
+//   * the digit of the reference plan is one PRMT (byte extract, selector in a register) instead of
+//     shift + mask + scale (the old kernel spent 4-5 instructions per digit use, three uses per key).
+//   * counters, ranks and slot bases are kept in BYTES (a key adds 4): the shared-memory address
+//     of a key's slot is rank + base + constant, no shift.
+//   * full tiles take branch-free load and scatter loops (the guard is hoisted out).
+//   * collision repair (template RANK): hardware MATCH.ANY over the few lanes a REDUX.OR bloom
+//     filter of the colliding digits selects, instead of a shuffle + ballot loop per collision
+//     group; its cost is per distinct value among the PARTICIPATING lanes, so it also replaces
+//     the 8-round ballot fallback for low-entropy digits.
+//   * the counter read-back / repair of item i overlaps the atomic of item i + 1 (software
+//     pipelining in source order; the warp-collective operations keep that order).
+//   * reduce-then-scan: the upsweep leaves, per tile, the exclusive prefix INSIDE its chunk, so a
+//     tile fetches 2 words per digit instead of 8.
+// MODE 0: onesweep (tickets + decoupled look-back)   MODE 1: reduce-then-scan scatter pass.
+// GENERIC = false: the reference's digit plan (shift = 8 * pass, mask = 0xFF, identity codec);
+// GENERIC = true: digit and codec from PassArgs (vrdxCudaCmdSortEx).
+// ------------------------------------------------------------------------------------------
+#ifndef VRDX_RANK_PIPELINE
+#define VRDX_RANK_PIPELINE 1  // 1: the read-back / repair of item i is issued after the atomic of item i + 1
+#endif
+#ifndef VRDX_RANK_SYNCWARP
+#define VRDX_RANK_SYNCWARP 1  // 1: __syncwarp() between a warp's atomics and the counter read-back; 0: compiler fence only
+#endif
+#ifndef VRDX_RANK
+#define VRDX_RANK 1  // 0: shuffle + ballot loop per collision group; 1: bloom + MATCH.ANY; 2: REDUX.MIN loop
+#endif
+
+// Digit of a key.  Reference plan: byte `pass` of the word, one PRMT with the selector 0x4440 | pass
+// (bytes 1..3 of the result come from the zero operand).  Generic plan: (k >> shift) & mask.
+// Orders a warp's shared-memory atomics of one item before its counter read-back, and that before the
+// atomics of the next item.
+__device__ __forceinline__ void RankFence() {
+#if VRDX_RANK_SYNCWARP
+  __syncwarp();
+#else
+  asm volatile("" ::: "memory");
+#endif
+}
+
+template <bool GENERIC>
+__device__ __forceinline__ uint32_t DigitOf(uint32_t k, uint32_t shift_or_sel, uint32_t mask) {
+  if (!GENERIC) return __byte_perm(k, 0u, shift_or_sel);
+  return (k >> shift_or_sel) & mask;
+}
+
+// Final rank (in bytes) of a key among the keys of its warp with the same digit: `old` is what the
+// returning atomicAdd(+4) gave this lane, `fin` the counter after all lanes of this item were
+// served.  ge = lanes >= this one.  A lane that was alone keeps old (fin - old == 4).
+template <int RANK>
+__device__ __forceinline__ uint32_t RepairRank(uint32_t d, uint32_t old, uint32_t fin, uint32_t ge) {
+  uint32_t r = old;
+  const bool flagged = fin - old > 4u;  // somebody was served after me: I am in a collision group
+  if (RANK == 1) {
+    // Every member of a group but the one served last is flagged.  A 32-bit bloom filter of the
+    // flagged digits (one REDUX.OR) finds that one too, plus a few false positives, and
+    // MATCH.ANY among those lanes only gives each its exact peers.
+    const uint32_t bit = 1u << (d & 31u);
+    const uint32_t bloom = __reduce_or_sync(0xffffffffu, flagged ? bit : 0u);
+    const bool cand = (bloom & bit) != 0u;
+    const uint32_t cmask = __ballot_sync(0xffffffffu, cand);
+    if (cand) {
+      const uint32_t peers = __match_any_sync(cmask, d);
+      r = fin - 4u * (uint32_t)__popc(peers & ge);  // a false positive has peers == itself: fin - 4 == old
+    }
+  } else {
+    uint32_t suspects = __ballot_sync(0xffffffffu, flagged);
+    if (suspects != 0u) {
+      if (__popc(suspects) > kRepairBallotThreshold) {
+        uint32_t peers = 0xffffffffu;
+#pragma unroll
+        for (int b = 0; b < kRadixBits; ++b) {
+          const bool bt = (d >> b) & 1u;
+          const uint32_t m = __ballot_sync(0xffffffffu, bt);
+          peers &= bt ? m : ~m;
+        }
+        r = fin - 4u * (uint32_t)__popc(peers & ge);
+      } else if (RANK == 2) {
+        uint32_t mine = flagged ? d : 0xffffffffu;
+        do {
+          const uint32_t dstar = __reduce_min_sync(0xffffffffu, mine);
+          const uint32_t peers = __ballot_sync(0xffffffffu, d == dstar);
+          if (d == dstar) {
+            r = fin - 4u * (uint32_t)__popc(peers & ge);
+            mine = 0xffffffffu;
+          }
+          suspects &= ~peers;
+        } while (suspects != 0u);
+      } else {
+        do {
+          const uint32_t dstar = __shfl_sync(0xffffffffu, d, __ffs(suspects) - 1);
+          const uint32_t peers = __ballot_sync(0xffffffffu, d == dstar);
+          if (d == dstar) r = fin - 4u * (uint32_t)__popc(peers & ge);
+          suspects &= ~peers;
+        } while (suspects != 0u);
+      }
+    }
+  }
+  return r;
+}
+
+template <class Cfg, int MODE, bool GENERIC, int RANK = VRDX_RANK>
 __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinCtas)
-OnesweepKernel(const PassArgs a) {
+PassKernel(const PassArgs a) {
   constexpr int THREADS = Cfg::kThreads;
   constexpr int IPT = Cfg::kItems;
   constexpr bool KV = Cfg::kKeyValue;
   constexpr int kWarps = Cfg::kWarps;
   constexpr int kTile = Cfg::kTile;
   constexpr int kLookBatch = Cfg::kLookBatch;
+  static_assert(MODE == 0 || MODE == 1, "onesweep or reduce-then-scan");
 
   extern __shared__ __align__(128) uint32_t smem[];
-  uint32_t* s_cnt = smem;                             // [kWarps][256] warp-private digit counters, later slot bases
+  uint32_t* s_cnt = smem;                             // [kWarps][256] warp-private digit counters (bytes), later slot bases
   uint32_t* s_keys = s_cnt + kWarps * kRadix;         // [kTile] tile reordered by digit
   uint32_t* s_vals = s_keys + kTile;                  // [kTile] (KV only)
   uint32_t* s_gbase = s_vals + (KV ? kTile : 0);      // [256] global slot of tile-local slot 0, per digit
@@ -519,9 +585,10 @@ OnesweepKernel(const PassArgs a) {
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const uint32_t shift = GENERIC ? a.shift : a.pass * kRadixBits;
+  const uint32_t pass = a.pass;
+  const uint32_t shift = GENERIC ? a.shift : (0x4440u | pass);  // reference plan: the PRMT selector of byte `pass`
   const uint32_t mask = GENERIC ? a.mask : (uint32_t)(kRadix - 1);
-  const KeyCodec cin = GENERIC ? a.codec_in : KeyCodec{0u, 0u, 0u};    // identity codecs fold away
+  const KeyCodec cin = GENERIC ? a.codec_in : KeyCodec{0u, 0u, 0u};
   const KeyCodec cout = GENERIC ? a.codec_out : KeyCodec{0u, 0u, 0u};
   const uint32_t n = ResolveCount(a.indirect, a.n_or_max);
   GridDepLaunch();
@@ -531,13 +598,10 @@ OnesweepKernel(const PassArgs a) {
     for (int j = tid; j < kWarps * kRadix / 4; j += THREADS) z[j] = make_uint4(0u, 0u, 0u, 0u);
   }
   GridDepWait();  // everything below reads what the previous kernel of this sort wrote
-  // Tile ids are handed out in arrival order so that every predecessor a tile may wait on in
-  // the look-back is already resident (forward progress without relying on blockIdx order).
-  // Keys-only onesweep pass 0 is order-free (see the ranking below): tiles claim their output
-  // ranges with global atomics, so it needs neither tickets nor the look-back chain.
+  // keys-only first pass of a sort over all 32 bits: no earlier order to preserve (see the ranking below)
   const bool order_free = !KV && a.order_free != 0u;
-  const bool unordered = (MODE != 1) && order_free;
-  if (MODE == 0 && !unordered && tid == 0) s_misc[8] = atomicAdd(&a.hdr->tickets[a.pass], 1u);  // MODE 1/2: blockIdx.x
+  const bool unordered = (MODE == 0) && order_free;
+  if (MODE == 0 && !unordered && tid == 0) s_misc[8] = atomicAdd(&a.hdr->tickets[pass], 1u);
   __syncthreads();
 
   const uint32_t tile = (MODE == 0 && !unordered) ? s_misc[8] : blockIdx.x;
@@ -547,10 +611,10 @@ OnesweepKernel(const PassArgs a) {
   const uint32_t tile_count = remaining < (uint32_t)kTile ? remaining : (uint32_t)kTile;
   const bool full = tile_count == (uint32_t)kTile;
 
-  if (MODE != 1 && a.status_next != nullptr && tid < kRadix) a.status_next[(size_t)tile * kRadix + tid] = 0;
+  if (MODE == 0 && a.status_next != nullptr && tid < kRadix) a.status_next[(size_t)tile * kRadix + tid] = 0;
 
   // ---- constant digit: a stable counting sort with one non-empty bucket is a copy --------------
-  if (a.hdr->pass_identity[a.pass]) {
+  if (a.hdr->pass_identity[pass]) {
     const uint32_t* kin = a.keys_in + tile_start;
     uint32_t* kout = a.keys_out + tile_start;
     uint32_t ck[IPT], cv[KV ? IPT : 1];
@@ -581,37 +645,62 @@ OnesweepKernel(const PassArgs a) {
 #pragma unroll
       for (int i = 0; i < IPT; ++i) key[i] = KeyIn(LdStream(kin + 32 * i), cin);
     } else {
-      // Tail tile: pad with the largest word so pads rank after every real key (the reference
-      // pads the same way, downsweep.slang:81,85); their slots are >= tile_count and never stored.
+      // tail tile: pads are the largest word, rank after every real key and are never stored
 #pragma unroll
       for (int i = 0; i < IPT; ++i)
         key[i] = (woff + 32 * i < tile_count) ? KeyIn(LdStream(kin + 32 * i), cin) : 0xFFFFFFFFu;
     }
   }
 
-  // ---- warp-level multi-split: rank of each key among equal digits inside its warp ---------
-  uint32_t rank[IPT];
-  {
-    uint32_t* cnt = s_cnt + warp * kRadix;
-    const uint32_t lt = LaneMaskLt();
-    if (order_free && full) {
-      // Keys-only, first pass of a sort over all 32 bits: there is no earlier order to preserve
-      // and equal keys are indistinguishable, so ANY bijective ranking inside a digit gives the
-      // same final output.  The value returned by the atomic is such a ranking: no read-back, no
-      // collision repair.  (Every later pass, every pass of a key-value or bit-sub-range sort, and
-      // the tail tile — whose pads must keep ranking after the real keys — are stable.)
+  // ---- warp-level multi-split: rank (bytes) of each key among equal digits inside its warp ----
+  // Ranks stay below 2^16 even after the slot base is added (kTile * 4 <= 2^16 is not required:
+  // kTile <= 2^14), so two of them share a register: 8 registers less than one per key.
+  uint32_t rank2[IPT / 2];
+  uint32_t* const row = s_cnt + warp * kRadix;
+  if (order_free && full) {
 #pragma unroll
-      for (int i = 0; i < IPT; ++i) rank[i] = atomicAdd(&cnt[(key[i] >> shift) & mask], 1u);
-    } else {
-#pragma unroll
-      for (int i = 0; i < IPT; ++i) {
-        rank[i] = WarpRankDigit(cnt, (key[i] >> shift) & mask, lt);
-      }
+    for (int i = 0; i < IPT; i += 2) {
+      const uint32_t r0 = atomicAdd(row + DigitOf<GENERIC>(key[i], shift, mask), 4u);
+      const uint32_t r1 = atomicAdd(row + DigitOf<GENERIC>(key[i + 1], shift, mask), 4u);
+      rank2[i / 2] = __byte_perm(r0, r1, 0x5410);
     }
+  } else {
+    const uint32_t ge = ~LaneMaskLt();
+#if VRDX_RANK_PIPELINE
+    uint32_t d_prev = 0, old_prev = 0, fin_prev = 0, r_even = 0;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const uint32_t d = DigitOf<GENERIC>(key[i], shift, mask);
+      volatile uint32_t* c = row + d;
+      const uint32_t old = atomicAdd(row + d, 4u);  // optimistic: exact if no other lane holds digit d
+      RankFence();
+      const uint32_t fin = *c;                      // all 32 increments of this item have landed
+      RankFence();
+      if (i > 0) {  // repair of the previous item overlaps the round trip above
+        const uint32_t r = RepairRank<RANK>(d_prev, old_prev, fin_prev, ge);
+        if ((i - 1) & 1) rank2[(i - 1) / 2] = __byte_perm(r_even, r, 0x5410); else r_even = r;
+      }
+      d_prev = d; old_prev = old; fin_prev = fin;
+    }
+    rank2[IPT / 2 - 1] = __byte_perm(r_even, RepairRank<RANK>(d_prev, old_prev, fin_prev, ge), 0x5410);
+#else
+    uint32_t r_even = 0;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const uint32_t d = DigitOf<GENERIC>(key[i], shift, mask);
+      volatile uint32_t* c = row + d;
+      const uint32_t old = atomicAdd(row + d, 4u);  // optimistic: exact if no other lane holds digit d
+      RankFence();
+      const uint32_t fin = *c;                      // all 32 increments of this item have landed
+      const uint32_t r = RepairRank<RANK>(d, old, fin, ge);
+      RankFence();
+      if (i & 1) rank2[i / 2] = __byte_perm(r_even, r, 0x5410); else r_even = r;
+    }
+#endif
   }
   __syncthreads();
 
-  // ---- per-digit: counts over warps, publish aggregate, tile-local exclusive scan -----------
+  // ---- per-digit: counts over warps, publish aggregate, tile-local exclusive scan (bytes) -----
   uint32_t digit_count = 0, digit_excl = 0;
   uint32_t wcount[kWarps];
   if (tid < kRadix) {
@@ -622,8 +711,8 @@ OnesweepKernel(const PassArgs a) {
       sum += wcount[w];
     }
     // pads were counted as the largest digit of this pass; they are not part of the data
-    digit_count = sum - (((uint32_t)tid == mask) ? ((uint32_t)kTile - tile_count) : 0u);
-    if (MODE != 1 && !unordered)
+    digit_count = (sum >> 2) - (((uint32_t)tid == mask) ? ((uint32_t)kTile - tile_count) : 0u);
+    if (MODE == 0 && !unordered)
       StRelaxed(a.status + (size_t)tile * kRadix + tid,
                 (tile == 0 ? kStatusPrefix : kStatusAggregate) | digit_count);
     const uint32_t incl = WarpInclusiveScan(sum, lane);
@@ -635,69 +724,57 @@ OnesweepKernel(const PassArgs a) {
   if (tid < kRadix) {
 #pragma unroll
     for (int w = 0; w < kRadix / 32; ++w) digit_excl += (w < warp) ? s_misc[w] : 0u;
-    // s_cnt becomes the tile-local slot of the first key of (warp, digit)
+    // s_cnt becomes the tile-local byte offset of the first key of (warp, digit)
     uint32_t run = digit_excl;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) {
       s_cnt[w * kRadix + tid] = run;
       run += wcount[w];
     }
-    // start the first batch of look-back loads now; it is consumed after the reorder below
     if (unordered) {
-      // claim [excl, excl + digit_count) of this digit's global run; the round trip overlaps the reorder
       look_s[0] = digit_count ? atomicAdd(&a.hdr->claim_cursor[tid], digit_count) : 0u;
-    } else if (MODE != 1) {
+    } else if (MODE == 0) {
 #pragma unroll
       for (int j = 0; j < kLookBatch; ++j) {
         const uint32_t t = (tile > (uint32_t)j) ? tile - 1 - j : 0u;
         look_s[j] = (tile > 0) ? LdRelaxed(a.status + (size_t)t * kRadix + tid) : 0u;
       }
     } else {
-      // reduce-then-scan: scanned chunk prefix + the rows of the earlier tiles of this chunk
-      const uint32_t chunk = tile / kSpineChunk;
-      const uint32_t in_chunk = tile % kSpineChunk;
-      const uint32_t* row = a.status + (size_t)chunk * kSpineChunk * kRadix + tid;
-      uint32_t part[kSpineChunk - 1];
-#pragma unroll
-      for (int j = 0; j < kSpineChunk - 1; ++j) part[j] = ((uint32_t)j < in_chunk) ? row[(size_t)j * kRadix] : 0u;  // all in flight at once
-      uint32_t acc = a.status_next[(size_t)chunk * kRadix + tid];
-#pragma unroll
-      for (int j = 0; j < kSpineChunk - 1; ++j) acc += part[j];
-      look_s[0] = acc;
+      // reduce-then-scan: scanned chunk prefix + this tile's exclusive prefix inside its chunk
+      look_s[0] = a.status_next[(size_t)(tile / kSpineChunk) * kRadix + tid] + a.status[(size_t)tile * kRadix + tid];
     }
   }
   __syncthreads();
 
   // ---- tile-local reorder through shared memory --------------------------------------------
   {
-    const uint32_t* base = s_cnt + warp * kRadix;
+    char* const keys_b = reinterpret_cast<char*>(s_keys);
+    uint32_t slot_b[KV ? IPT : 1];  // byte offset of each key's slot (kept for the values only)
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
-      const uint32_t d = (key[i] >> shift) & mask;
-      rank[i] += base[d];
-      if (!Cfg::kPaired) s_keys[rank[i]] = key[i];
+      const uint32_t r = (i & 1) ? (rank2[i / 2] >> 16) : (rank2[i / 2] & 0xFFFFu);
+      const uint32_t sb = r + row[DigitOf<GENERIC>(key[i], shift, mask)];
+      *reinterpret_cast<uint32_t*>(keys_b + sb) = key[i];
+      if (KV) slot_b[i] = sb;
     }
     if (KV) {
       // values are fetched only now, so they do not occupy registers during the ranking
       const uint32_t* vin = a.vals_in + tile_start + woff;
       uint32_t val[IPT];
+      if (full) {
 #pragma unroll
-      for (int i = 0; i < IPT; ++i) val[i] = (full || woff + 32 * i < tile_count) ? LdStream(vin + 32 * i) : 0u;
-      if (Cfg::kPaired) {
-        // keys were not stored above (see kPaired there): one 64-bit store per pair
-        uint2* s_kv = reinterpret_cast<uint2*>(s_keys);
-#pragma unroll
-        for (int i = 0; i < IPT; ++i) s_kv[rank[i]] = make_uint2(key[i], val[i]);
+        for (int i = 0; i < IPT; ++i) val[i] = LdStream(vin + 32 * i);
       } else {
 #pragma unroll
-        for (int i = 0; i < IPT; ++i) s_vals[rank[i]] = val[i];
+        for (int i = 0; i < IPT; ++i) val[i] = (woff + 32 * i < tile_count) ? LdStream(vin + 32 * i) : 0u;
       }
+      char* const vals_b = reinterpret_cast<char*>(s_vals);
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) *reinterpret_cast<uint32_t*>(vals_b + slot_b[i]) = val[i];
     }
   }
 
-  // ---- decoupled look-back: exclusive prefix of this digit over all earlier tiles ------------
-  // kLookBatch predecessor cells are in flight per round trip; they are consumed strictly in
-  // order (nearest tile first) and the walk stops at the first inclusive prefix.
+  // ---- global offsets of the digit runs ----------------------------------------------------
   if (tid < kRadix) {
     uint32_t excl = 0;
     if (unordered || MODE == 1) {
@@ -707,216 +784,28 @@ OnesweepKernel(const PassArgs a) {
       StRelaxed(a.status + (size_t)tile * kRadix + tid, kStatusPrefix | (excl + digit_count));
     }
     // global slot of tile-local slot 0 for this digit (mod 2^32 arithmetic)
-    s_gbase[tid] = a.hdr->global_hist[a.pass][tid] + excl - digit_excl;
+    s_gbase[tid] = a.hdr->global_hist[pass][tid] + excl - (digit_excl >> 2);
   }
   __syncthreads();
 
   // ---- scatter: consecutive threads write consecutive slots of a digit run -------------------
-#pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const uint32_t slot = i * THREADS + tid;
-    if (Cfg::kPaired) {
-      const uint2 kv = reinterpret_cast<const uint2*>(s_keys)[slot];
-      const uint32_t g = s_gbase[(kv.x >> shift) & mask] + slot;
-      if (full || slot < tile_count) {
-        a.keys_out[g] = KeyOut(kv.x, cout);
-        a.vals_out[g] = kv.y;
-      }
-    } else {
-      const uint32_t k = s_keys[slot];
-      const uint32_t g = s_gbase[(k >> shift) & mask] + slot;
-      if (full || slot < tile_count) {
-        a.keys_out[g] = KeyOut(k, cout);
-        if (KV) a.vals_out[g] = s_vals[slot];
-      }
-    }
-  }
-  StampEnd(a.ts_end);
-}
-
-// ------------------------------------------------------------------------------------------
-// OnesweepClusterKernel — onesweep with ONE look-back per thread-block cluster.
-//
-// Measured on B200 at N = 2^28: the look-back-free scatter pass (reduce-then-scan downsweep)
-// takes 0.92 ms, the same pass with a per-tile decoupled look-back 1.24 ms.  The look-back depth
-// is D ~ lambda * (tiles per cycle): with ~440 tiles in flight and ~700 cycles per L2 round trip a
-// tile has to sum ~12 predecessor cells, 1 KB each, while its CTA waits.  Clusters shrink the
-// chain: the CLUSTER CTAs of a cluster sort CLUSTER consecutive tiles, exchange their per-digit
-// counts through distributed shared memory, and the cluster appears on the global chain as ONE
-// participant (one status row, one ticket).  The 256 digits are split across the CTAs of the
-// cluster, so each CTA runs the look-back for 256/CLUSTER digits only, in its last warp(s), while
-// all other warps reorder the tile.  Chain participants, look-back depth, status traffic and
-// status memory all drop by CLUSTER x.
-// ------------------------------------------------------------------------------------------
-template <class Cfg, int CLUSTER>
-__global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinCtas)
-OnesweepClusterKernel(const PassArgs a) {
-  namespace cg = cooperative_groups;
-  constexpr int THREADS = Cfg::kThreads;
-  constexpr int IPT = Cfg::kItems;
-  constexpr bool KV = Cfg::kKeyValue;
-  constexpr int kWarps = Cfg::kWarps;
-  constexpr int kTile = Cfg::kTile;
-  constexpr int kLookBatch = Cfg::kLookBatch;
-  constexpr int kSlice = kRadix / CLUSTER;  // digits whose look-back this CTA runs
-  static_assert(kRadix % CLUSTER == 0 && kSlice % 32 == 0 && kSlice <= THREADS, "digit slice must be whole warps");
-
-  extern __shared__ __align__(128) uint32_t smem[];
-  uint32_t* s_cnt = smem;                             // [kWarps][256]
-  uint32_t* s_keys = s_cnt + kWarps * kRadix;         // [kTile]
-  uint32_t* s_vals = s_keys + kTile;                  // [kTile] (KV only)
-  uint32_t* s_gbase = s_vals + (KV ? kTile : 0);      // [256]
-  uint32_t* s_misc = s_gbase + kRadix;                // [0..7] warp totals, [8] cluster ticket (rank 0)
-  __shared__ uint32_t s_tot[kRadix];                  // this tile's digit counts, read by the slice owners over DSMEM
-  __shared__ uint32_t s_ext[kRadix];                  // written by the slice owners over DSMEM: keys of this digit in all earlier tiles
-
-  cg::cluster_group cluster = cg::this_cluster();
-  const uint32_t crank = cluster.block_rank();
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int warp = tid >> 5;
-  const uint32_t shift = a.pass * kRadixBits;
-  const uint32_t n = ResolveCount(a.indirect, a.n_or_max);
-
-  GridDepLaunch();
-  {
-    uint4* z = reinterpret_cast<uint4*>(s_cnt);
-#pragma unroll
-    for (int j = tid; j < kWarps * kRadix / 4; j += THREADS) z[j] = make_uint4(0u, 0u, 0u, 0u);
-  }
-  GridDepWait();
-  // one ticket per cluster, drawn by rank 0 and read by the other CTAs over DSMEM
-  if (crank == 0 && tid == 0) s_misc[8] = atomicAdd(&a.hdr->tickets[a.pass], 1u);
-  cluster.sync();
-  const uint32_t ctile = *cluster.map_shared_rank(&s_misc[8], 0);
-  const uint64_t cluster_start = (uint64_t)ctile * CLUSTER * kTile;
-  if (cluster_start >= n) {  // whole cluster past the (indirect) count: retire together
-    cluster.sync();          // rank 0's shared memory must outlive the reads above
-    return;
-  }
-  const uint32_t tile = ctile * CLUSTER + crank;
-  const uint64_t tile_start = (uint64_t)tile * kTile;
-  const bool active = tile_start < n;  // CTAs past the count still serve their digit slice
-  const uint32_t remaining = active ? (uint32_t)(n - tile_start) : 0u;
-  const uint32_t tile_count = remaining < (uint32_t)kTile ? remaining : (uint32_t)kTile;
-  const bool full = tile_count == (uint32_t)kTile;
-
-  // ---- load + warp-level multi-split (identical to OnesweepKernel) ---------------------------
-  uint32_t key[IPT];
-  uint32_t rank[IPT];
-  const uint32_t woff = warp * 32 * IPT + lane;
-  if (active) {
-    const uint32_t* kin = a.keys_in + tile_start + woff;
-    if (full) {
-#pragma unroll
-      for (int i = 0; i < IPT; ++i) key[i] = LdStream(kin + 32 * i);
-    } else {
-#pragma unroll
-      for (int i = 0; i < IPT; ++i) key[i] = (woff + 32 * i < tile_count) ? LdStream(kin + 32 * i) : 0xFFFFFFFFu;
-    }
-    uint32_t* cnt = s_cnt + warp * kRadix;
-    const uint32_t lt = LaneMaskLt();
-#pragma unroll
-    for (int i = 0; i < IPT; ++i) rank[i] = WarpRankDigit(cnt, (key[i] >> shift) & 0xFFu, lt);
-  }
-  __syncthreads();
-
-  // ---- per-digit: counts over warps, tile-local exclusive scan --------------------------------
-  uint32_t digit_count = 0, digit_excl = 0;
-  uint32_t wcount[kWarps];
-  if (tid < kRadix) {
-    uint32_t sum = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-      wcount[w] = s_cnt[w * kRadix + tid];
-      sum += wcount[w];
-    }
-    digit_count = sum - ((active && tid == kRadix - 1) ? ((uint32_t)kTile - tile_count) : 0u);
-    const uint32_t incl = WarpInclusiveScan(sum, lane);
-    if (lane == 31) s_misc[warp] = incl;
-    digit_excl = incl - sum;
-  }
-  __syncthreads();
-  if (tid < kRadix) {
-#pragma unroll
-    for (int w = 0; w < kRadix / 32; ++w) digit_excl += (w < warp) ? s_misc[w] : 0u;
-    uint32_t run = digit_excl;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-      s_cnt[w * kRadix + tid] = run;
-      run += wcount[w];
-    }
-    s_tot[tid] = digit_count;
-  }
-  cluster.sync();  // every tile's digit counts are visible cluster-wide
-
-  // ---- slice owners: cluster aggregate, first look-back loads -----------------------------------
-  const bool is_slice = tid >= THREADS - kSlice;
-  const int my_digit = (int)crank * kSlice + (tid - (THREADS - kSlice));
-  uint32_t tot[CLUSTER];
-  uint32_t ctotal = 0;
-  uint32_t look_s[kLookBatch];
-  if (is_slice) {
-#pragma unroll
-    for (int r = 0; r < CLUSTER; ++r) {
-      tot[r] = *cluster.map_shared_rank(&s_tot[my_digit], r);
-      ctotal += tot[r];
-    }
-    StRelaxed(a.status + (size_t)ctile * kRadix + my_digit,
-              (ctile == 0 ? kStatusPrefix : kStatusAggregate) | ctotal);
-    if (a.status_next != nullptr) a.status_next[(size_t)ctile * kRadix + my_digit] = 0;
-#pragma unroll
-    for (int j = 0; j < kLookBatch; ++j) {
-      const uint32_t t = (ctile > (uint32_t)j) ? ctile - 1 - j : 0u;
-      look_s[j] = (ctile > 0) ? LdRelaxed(a.status + (size_t)t * kRadix + my_digit) : 0u;
-    }
-  }
-
-  // ---- tile-local reorder through shared memory -------------------------------------------------
-  if (active) {
-    const uint32_t* base = s_cnt + warp * kRadix;
-#pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      rank[i] += base[(key[i] >> shift) & 0xFFu];
-      s_keys[rank[i]] = key[i];
-    }
-    if (KV) {
-      const uint32_t* vin = a.vals_in + tile_start + woff;
-      uint32_t val[IPT];
-#pragma unroll
-      for (int i = 0; i < IPT; ++i) val[i] = (full || woff + 32 * i < tile_count) ? LdStream(vin + 32 * i) : 0u;
-#pragma unroll
-      for (int i = 0; i < IPT; ++i) s_vals[rank[i]] = val[i];
-    }
-  }
-
-  // ---- slice owners: look-back over earlier CLUSTERS, then hand every tile its offset -----------
-  if (is_slice) {
-    uint32_t excl = 0;
-    if (ctile > 0) {
-      excl = LookBack<kLookBatch>(a.status, ctile, my_digit, look_s);
-      StRelaxed(a.status + (size_t)ctile * kRadix + my_digit, kStatusPrefix | (excl + ctotal));
-    }
-#pragma unroll
-    for (int r = 0; r < CLUSTER; ++r) {
-      *cluster.map_shared_rank(&s_ext[my_digit], r) = excl;  // keys of this digit in all earlier tiles
-      excl += tot[r];
-    }
-  }
-  cluster.sync();  // offsets delivered; no distributed shared-memory access after this point
-
-  if (tid < kRadix) s_gbase[tid] = a.hdr->global_hist[a.pass][tid] + s_ext[tid] - digit_excl;
-  __syncthreads();
-
-  // ---- scatter ----------------------------------------------------------------------------------
-  if (active) {
+  if (full) {
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
       const uint32_t slot = i * THREADS + tid;
       const uint32_t k = s_keys[slot];
-      const uint32_t g = s_gbase[(k >> shift) & 0xFFu] + slot;
-      if (full || slot < tile_count) {
-        a.keys_out[g] = k;
+      const uint32_t g = s_gbase[DigitOf<GENERIC>(k, shift, mask)] + slot;
+      a.keys_out[g] = KeyOut(k, cout);
+      if (KV) a.vals_out[g] = s_vals[slot];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const uint32_t slot = i * THREADS + tid;
+      if (slot < tile_count) {
+        const uint32_t k = s_keys[slot];
+        const uint32_t g = s_gbase[DigitOf<GENERIC>(k, shift, mask)] + slot;
+        a.keys_out[g] = KeyOut(k, cout);
         if (KV) a.vals_out[g] = s_vals[slot];
       }
     }
@@ -941,7 +830,9 @@ OnesweepClusterKernel(const PassArgs a) {
 // ------------------------------------------------------------------------------------------
 constexpr int kUpsweepThreads = 256;
 
-template <int TILE>
+// EXCL: tile_hist[tile][d] holds the number of digit-d keys in the EARLIER tiles of the same chunk (what
+// PassKernel<.., 1> adds to the chunk prefix) instead of the tile's own count (OnesweepKernel<.., 1>).
+template <int TILE, bool EXCL = false>
 __global__ void __launch_bounds__(kUpsweepThreads)
 UpsweepKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t shift, uint32_t mask,
               const KeyCodec codec_in, const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ tile_hist,
@@ -985,7 +876,7 @@ UpsweepKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t
     __syncthreads();  // one barrier per tile: the two histograms alternate
     const uint32_t c = hh[tid];
     hh[tid] = 0;      // ready for tile + 2 (the next tile uses the other buffer; barrier above orders it)
-    tile_hist[(size_t)tile * kRadix + tid] = c;
+    tile_hist[(size_t)tile * kRadix + tid] = EXCL ? chunk_acc : c;
     chunk_acc += c;
   }
   chunk_sums[(size_t)blockIdx.x * kRadix + tid] = chunk_acc;
@@ -1080,282 +971,6 @@ SpineApplyKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint3
     }
   }
   StampEnd(ts_end);
-}
-
-// ------------------------------------------------------------------------------------------
-// OnesweepTmaKernel — the same pass as OnesweepKernel, as a PERSISTENT kernel with TMA staging.
-//
-// The grid is one wave of co-resident CTAs (SM count x CTAs/SM).  Each CTA loops over tiles it
-// draws from the ticket counter; the raw keys of a tile are brought into shared memory by ONE
-// bulk asynchronous copy (cp.async.bulk global -> shared, completion on an mbarrier; SASS UBLKCP)
-// issued a whole tile ahead into the other half of a double buffer, so neither the global-load
-// latency nor the ticket's atomic round trip is on the critical path, no warp sleeps on a
-// scoreboard for its keys, and no CTA launch/teardown happens between tiles.  The staging buffer
-// of the current tile is reused as the reorder buffer once every thread holds its keys in
-// registers.  Key-value sorts stage the tile's values the same way (single buffer, issued when
-// the tile starts, consumed at the reorder).  Needs 16-byte aligned key/value/storage
-// addresses (cp.async.bulk); the host falls back to OnesweepKernel otherwise.  Tail (partial)
-// tiles are loaded with guarded scalar loads.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t SmemAddr(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void MbarInit(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(SmemAddr(bar)), "r"(count));
-}
-__device__ __forceinline__ void MbarExpectTx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(SmemAddr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void MbarWait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "VRDX_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@!p bra VRDX_WAIT;\n\t}"
-      ::"r"(SmemAddr(bar)), "r"(parity) : "memory");
-}
-// global -> shared bulk copy (TMA), bytes a multiple of 16, both addresses 16-byte aligned.
-__device__ __forceinline__ void TmaLoad1D(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  uint64_t policy;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-      ::"r"(SmemAddr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(SmemAddr(bar)), "l"(policy) : "memory");
-}
-__device__ __forceinline__ void FenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-template <int THREADS, int IPT, bool KV, int MIN_CTAS, int LOOK_BATCH = 4>
-struct TmaPassConfig {
-  static constexpr int kLookBatch = LOOK_BATCH;
-  static constexpr int kThreads = THREADS;
-  static constexpr int kItems = IPT;
-  static constexpr int kMinCtas = MIN_CTAS;
-  static constexpr bool kKeyValue = KV;
-  static constexpr int kWarps = THREADS / 32;
-  static constexpr int kTile = THREADS * IPT;
-  static constexpr int kMiscWords = 32;
-  // stage[2][kTile] | vstage[kTile] (KV) | cnt[kWarps][256] | gbase[256] | misc (tile ids, mbarriers)
-  static constexpr size_t kSmemBytes =
-      sizeof(uint32_t) * ((size_t)kTile * (KV ? 3 : 2) + (size_t)kWarps * kRadix + kRadix + kMiscWords);
-  static_assert(THREADS % 32 == 0 && THREADS >= kRadix && THREADS <= 1024, "one thread per digit is assumed");
-  static_assert(kTile % 4 == 0 && kTile <= (1 << 16), "tile bytes must be a multiple of 16");
-};
-
-// MODE 0: onesweep (tickets + decoupled look-back).  MODE 1: scatter pass of reduce-then-scan —
-// tiles are strided statically over the persistent CTAs (tile = blockIdx.x + k * gridDim.x) and
-// `a.status` holds the exclusive per-tile digit prefixes, so there is no inter-CTA ordering to
-// respect and the prefetch distance costs nothing.
-template <class Cfg, int MODE = 0>
-__global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinCtas)
-OnesweepTmaKernel(const PassArgs a) {
-  constexpr int THREADS = Cfg::kThreads;
-  constexpr int IPT = Cfg::kItems;
-  constexpr bool KV = Cfg::kKeyValue;
-  constexpr int kWarps = Cfg::kWarps;
-  constexpr int kTile = Cfg::kTile;
-  constexpr uint32_t kTileBytes = kTile * sizeof(uint32_t);
-  constexpr int kLookBatch = Cfg::kLookBatch;
-  constexpr int kProducer = THREADS - 1;  // lane 31 of the last warp: idle during the per-digit phases when THREADS > 256
-
-  extern __shared__ __align__(128) uint32_t smem[];
-  uint32_t* s_stage = smem;                                   // [2][kTile] raw tile, then the tile reordered by digit
-  uint32_t* s_vstage = s_stage + 2 * kTile;                   // [kTile] values (KV only)
-  uint32_t* s_cnt = s_vstage + (KV ? kTile : 0);              // [kWarps][256]
-  uint32_t* s_gbase = s_cnt + kWarps * kRadix;                // [256]
-  uint32_t* s_misc = s_gbase + kRadix;                        // [0..7] warp totals, [8..9] tile id per slot
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_misc + 16); // [0..1] key stages, [2] value stage
-
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int warp = tid >> 5;
-  const uint32_t shift = a.pass * kRadixBits;
-  const uint32_t n = ResolveCount(a.indirect, a.n_or_max);
-  const uint32_t lt = LaneMaskLt();
-
-  // Producer: draw a tile id and, if it is a full tile, start its bulk copy into `slot`.
-  auto fetch_tile = [&](int slot, uint32_t tile) {
-    s_misc[8 + slot] = tile;
-    const uint64_t start = (uint64_t)tile * kTile;
-    if (start + kTile <= (uint64_t)n) {
-      MbarExpectTx(&s_bar[slot], kTileBytes);
-      TmaLoad1D(s_stage + slot * kTile, a.keys_in + start, kTileBytes, &s_bar[slot]);
-    }
-  };
-
-  GridDepLaunch();
-  GridDepWait();
-  if (tid == kProducer) {
-    MbarInit(&s_bar[0], 1);
-    MbarInit(&s_bar[1], 1);
-    MbarInit(&s_bar[2], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    FenceProxyAsync();
-    const uint32_t t0 = (MODE == 0) ? atomicAdd(&a.hdr->tickets[a.pass], 1u) : blockIdx.x;
-    fetch_tile(0, t0);
-    const uint32_t t1 = (MODE == 0) ? atomicAdd(&a.hdr->tickets[a.pass], 1u) : blockIdx.x + gridDim.x;
-    fetch_tile(1, t1);
-  }
-  __syncthreads();
-
-  for (uint32_t iter = 0;; ++iter) {
-    const int slot = iter & 1;
-    uint32_t* stage = s_stage + slot * kTile;
-    const uint32_t tile = s_misc[8 + slot];
-    const uint64_t tile_start = (uint64_t)tile * kTile;
-    if (tile_start >= n) break;  // tickets are monotonic: every later tile of this CTA is out of range too
-    const uint32_t remaining = (uint32_t)(n - tile_start);
-    const uint32_t tile_count = remaining < (uint32_t)kTile ? remaining : (uint32_t)kTile;
-    const bool full = tile_count == (uint32_t)kTile;
-
-    // values of this tile: one bulk copy, consumed at the reorder (its latency hides behind the ranking)
-    if (KV && full && tid == kProducer) {
-      MbarExpectTx(&s_bar[2], kTileBytes);
-      TmaLoad1D(s_vstage, a.vals_in + tile_start, kTileBytes, &s_bar[2]);
-    }
-    {
-      uint4* z = reinterpret_cast<uint4*>(s_cnt);
-#pragma unroll
-      for (int j = tid; j < kWarps * kRadix / 4; j += THREADS) z[j] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    if (MODE == 0 && a.status_next != nullptr && tid < kRadix) a.status_next[(size_t)tile * kRadix + tid] = 0;
-
-    // ---- keys: shared-memory stage -> registers (warp-striped, conflict-free) -------------------
-    uint32_t key[IPT];
-    const uint32_t woff = warp * 32 * IPT + lane;
-    if (full) {
-      MbarWait(&s_bar[slot], (iter >> 1) & 1u);
-#pragma unroll
-      for (int i = 0; i < IPT; ++i) key[i] = stage[woff + 32 * i];
-    } else {
-      const uint32_t* kin = a.keys_in + tile_start + woff;
-#pragma unroll
-      for (int i = 0; i < IPT; ++i) key[i] = (woff + 32 * i < tile_count) ? LdStream(kin + 32 * i) : 0xFFFFFFFFu;
-    }
-    __syncthreads();  // counters zeroed; every thread holds its keys, so `stage` may be overwritten
-
-    // ---- warp-level multi-split ---------------------------------------------------------------
-    uint32_t rank[IPT];
-    {
-      uint32_t* cnt = s_cnt + warp * kRadix;
-#pragma unroll
-      for (int i = 0; i < IPT; ++i) rank[i] = WarpRankDigit(cnt, (key[i] >> shift) & 0xFFu, lt);
-    }
-    __syncthreads();
-
-    // ---- per-digit: counts over warps, publish aggregate, tile-local exclusive scan -------------
-    uint32_t digit_count = 0, digit_excl = 0;
-    uint32_t wcount[kWarps];
-    if (tid < kRadix) {
-      uint32_t sum = 0;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) {
-        wcount[w] = s_cnt[w * kRadix + tid];
-        sum += wcount[w];
-      }
-      digit_count = sum - ((tid == kRadix - 1) ? ((uint32_t)kTile - tile_count) : 0u);
-      if (MODE == 0)
-        StRelaxed(a.status + (size_t)tile * kRadix + tid,
-                  (tile == 0 ? kStatusPrefix : kStatusAggregate) | digit_count);
-      const uint32_t incl = WarpInclusiveScan(sum, lane);
-      if (lane == 31) s_misc[warp] = incl;
-      digit_excl = incl - sum;
-    }
-    __syncthreads();
-    uint32_t look_s[kLookBatch];
-    uint32_t next_ticket = 0;
-    if (tid < kRadix) {
-#pragma unroll
-      for (int w = 0; w < kRadix / 32; ++w) digit_excl += (w < warp) ? s_misc[w] : 0u;
-      uint32_t run = digit_excl;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) {
-        s_cnt[w * kRadix + tid] = run;
-        run += wcount[w];
-      }
-      if (MODE == 0) {
-#pragma unroll
-        for (int j = 0; j < kLookBatch; ++j) {
-          const uint32_t t = (tile > (uint32_t)j) ? tile - 1 - j : 0u;
-          look_s[j] = (tile > 0) ? LdRelaxed(a.status + (size_t)t * kRadix + tid) : 0u;
-        }
-      } else {
-        const uint32_t chunk = tile / kSpineChunk;
-        const uint32_t in_chunk = tile % kSpineChunk;
-        const uint32_t* row = a.status + (size_t)chunk * kSpineChunk * kRadix + tid;
-        uint32_t part[kSpineChunk - 1];
-#pragma unroll
-        for (int j = 0; j < kSpineChunk - 1; ++j) part[j] = ((uint32_t)j < in_chunk) ? row[(size_t)j * kRadix] : 0u;
-        uint32_t acc = a.status_next[(size_t)chunk * kRadix + tid];
-#pragma unroll
-        for (int j = 0; j < kSpineChunk - 1; ++j) acc += part[j];
-        look_s[0] = acc;
-      }
-    }
-    // the id of the tile that will replace this one is drawn here, off the critical path
-    if (tid == kProducer)
-      next_ticket = (MODE == 0) ? atomicAdd(&a.hdr->tickets[a.pass], 1u) : tile + 2u * gridDim.x;
-    __syncthreads();
-
-    // ---- tile-local reorder through shared memory (into the stage this tile arrived in) ---------
-    {
-      const uint32_t* base = s_cnt + warp * kRadix;
-#pragma unroll
-      for (int i = 0; i < IPT; ++i) {
-        rank[i] += base[(key[i] >> shift) & 0xFFu];
-        stage[rank[i]] = key[i];
-      }
-    }
-    if (KV) {
-      uint32_t val[IPT];
-      if (full) {
-        MbarWait(&s_bar[2], iter & 1u);
-#pragma unroll
-        for (int i = 0; i < IPT; ++i) val[i] = s_vstage[woff + 32 * i];
-      } else {
-        const uint32_t* vin = a.vals_in + tile_start + woff;
-#pragma unroll
-        for (int i = 0; i < IPT; ++i) val[i] = (woff + 32 * i < tile_count) ? LdStream(vin + 32 * i) : 0u;
-      }
-      __syncthreads();  // every thread holds its values before the buffer is permuted in place
-#pragma unroll
-      for (int i = 0; i < IPT; ++i) s_vstage[rank[i]] = val[i];
-    }
-
-    // ---- decoupled look-back --------------------------------------------------------------------
-    if (tid < kRadix) {
-      uint32_t excl = 0;
-      if (MODE == 0) {
-        if (tile > 0) {
-          excl = LookBack<kLookBatch>(a.status, tile, tid, look_s);
-          StRelaxed(a.status + (size_t)tile * kRadix + tid, kStatusPrefix | (excl + digit_count));
-        }
-      } else {
-        excl = look_s[0];
-      }
-      s_gbase[tid] = a.hdr->global_hist[a.pass][tid] + excl - digit_excl;
-    }
-    __syncthreads();
-
-    // ---- scatter --------------------------------------------------------------------------------
-#pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      const uint32_t slot_i = i * THREADS + tid;
-      const uint32_t k = stage[slot_i];
-      const uint32_t g = s_gbase[(k >> shift) & 0xFFu] + slot_i;
-      if (full || slot_i < tile_count) {
-        a.keys_out[g] = k;
-        if (KV) a.vals_out[g] = s_vstage[slot_i];
-      }
-    }
-    __syncthreads();  // the stage, the value buffer and the per-digit tables are free again
-
-    if (tid == kProducer) {
-      FenceProxyAsync();  // order the generic-proxy accesses above before the async-proxy refill
-      fetch_tile(slot, next_ticket);
-    }
-    // s_misc[8+slot] is next read two iterations from now, after several barriers
-  }
-  StampEnd(a.ts_end);
 }
 
 // CopyBackKernel — a sort with an odd number of passes (bit sub-range, extension) ends in the

@@ -22,7 +22,11 @@ def _as_i32(t: torch.Tensor) -> torch.Tensor:
 
 
 class Sorter:
-    """One ``VrdxSorter`` plus a grow-only storage buffer (the caller-owned scratch)."""
+    """One ``VrdxSorter`` plus grow-only storage buffers (the caller-owned scratch), one per CUDA stream
+    that sorts were enqueued on: the storage holds per-sort state (header, tables, ping-pong halves), so
+    two sorts in flight on different streams must not share it (the C API leaves that to the caller, this
+    wrapper must not hide a race).  Each buffer is allocated under the stream it serves, which makes the
+    caching allocator's reuse of a regrown buffer stream-ordered."""
 
     def __init__(self, device: int | torch.device = 0, algorithm: int = api.VRDX_CUDA_ALGORITHM_AUTO,
                  tile_load: int = api.VRDX_CUDA_TILE_LOAD_AUTO, reserved=None):
@@ -36,7 +40,7 @@ class Sorter:
         if res != api.VK_SUCCESS:
             raise RuntimeError(f"vrdxCreateSorter failed with VkResult {res}")
         self.handle = handle
-        self._storage: torch.Tensor | None = None
+        self._storage: dict[int, torch.Tensor] = {}
 
     # ------------------------------------------------------------------ lifetime
     def close(self) -> None:
@@ -44,7 +48,7 @@ class Sorter:
             torch.cuda.synchronize(self.device)
             api.vrdxDestroySorter(self.handle)
             self.handle = None
-            self._storage = None
+            self._storage = {}
 
     def __del__(self):  # best effort
         try:
@@ -57,12 +61,18 @@ class Sorter:
         fn = api.vrdxGetSorterKeyValueStorageRequirements if key_value else api.vrdxGetSorterStorageRequirements
         return fn(self.handle, max_count)
 
-    def storage_for(self, max_count: int, key_value: bool) -> torch.Tensor:
-        need = self.storage_requirements(max_count, key_value).size
-        if self._storage is None or self._storage.numel() < need:
-            self._storage = None
-            self._storage = torch.empty(need, dtype=torch.uint8, device=self.device)
-        return self._storage
+    def storage_for(self, max_count: int, key_value: bool, stream=None) -> torch.Tensor:
+        return self._scratch(int(self.storage_requirements(max_count, key_value).size), stream)
+
+    def _scratch(self, need: int, stream=None) -> torch.Tensor:
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        cur = self._storage.get(st.cuda_stream)
+        if cur is None or cur.numel() < need:
+            self._storage.pop(st.cuda_stream, None)
+            with torch.cuda.stream(st):
+                cur = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._storage[st.cuda_stream] = cur
+        return cur
 
     # ------------------------------------------------------------------ sorts (in place)
     def _stream(self, stream):
@@ -79,7 +89,7 @@ class Sorter:
         """vrdxCmdSort: sort keys[0:count] ascending as unsigned 32-bit, in place."""
         k = _as_i32(keys)
         n = k.numel() if count is None else int(count)
-        st = storage if storage is not None else self.storage_for(n, False)
+        st = storage if storage is not None else self.storage_for(n, False, stream)
         api.vrdxCmdSort(self._stream(stream), self.handle, n, k.data_ptr(), 0, st.data_ptr(), 0,
                         query_pool, query)
         self.check()
@@ -90,7 +100,7 @@ class Sorter:
         """vrdxCmdSortKeyValue: stable sort of (key, value) pairs by key, in place."""
         k, v = _as_i32(keys), _as_i32(values)
         n = k.numel() if count is None else int(count)
-        st = storage if storage is not None else self.storage_for(n, True)
+        st = storage if storage is not None else self.storage_for(n, True, stream)
         api.vrdxCmdSortKeyValue(self._stream(stream), self.handle, n, k.data_ptr(), 0, v.data_ptr(), 0,
                                 st.data_ptr(), 0, query_pool, query)
         self.check()
@@ -101,7 +111,7 @@ class Sorter:
         """vrdxCmdSortIndirect: the element count is read from device memory at sort time."""
         k = _as_i32(keys)
         m = k.numel() if max_count is None else int(max_count)
-        st = storage if storage is not None else self.storage_for(m, False)
+        st = storage if storage is not None else self.storage_for(m, False, stream)
         api.vrdxCmdSortIndirect(self._stream(stream), self.handle, m, count_buffer.data_ptr(), count_offset,
                                 k.data_ptr(), 0, st.data_ptr(), 0, query_pool, query)
         self.check()
@@ -112,7 +122,7 @@ class Sorter:
                                 query: int = 0) -> None:
         k, v = _as_i32(keys), _as_i32(values)
         m = k.numel() if max_count is None else int(max_count)
-        st = storage if storage is not None else self.storage_for(m, True)
+        st = storage if storage is not None else self.storage_for(m, True, stream)
         api.vrdxCmdSortKeyValueIndirect(self._stream(stream), self.handle, m, count_buffer.data_ptr(),
                                         count_offset, k.data_ptr(), 0, v.data_ptr(), 0, st.data_ptr(), 0,
                                         query_pool, query)
@@ -132,7 +142,7 @@ class Sorter:
         k = keys.view(torch.int32) if keys.dtype != torch.int32 else keys
         v = _as_i32(values) if values is not None else None
         m = k.numel() if max_count is None else int(max_count)
-        st = storage if storage is not None else self.storage_for(m, v is not None)
+        st = storage if storage is not None else self.storage_for(m, v is not None, stream)
         info = api.make_key_info(key_type, api.VRDX_CUDA_SORT_ORDER_DESCENDING if descending
                                  else api.VRDX_CUDA_SORT_ORDER_ASCENDING, begin_bit, end_bit)
         api.vrdxCudaCmdSortEx(self._stream(stream), self.handle, info, m,
@@ -152,11 +162,7 @@ class Sorter:
             raise TypeError(f"keys must be a 64-bit type, got {keys.dtype}")
         m = keys.numel() if max_count is None else int(max_count)
         if storage is None:
-            need = int(api.vrdxCudaGetSorterKeys64StorageRequirements(self.handle, m).size)
-            if self._storage is None or self._storage.numel() < need:
-                self._storage = None
-                self._storage = torch.empty(need, dtype=torch.uint8, device=self.device)
-            storage = self._storage
+            storage = self._scratch(int(api.vrdxCudaGetSorterKeys64StorageRequirements(self.handle, m).size), stream)
         info = api.make_key_info(key_type, api.VRDX_CUDA_SORT_ORDER_DESCENDING if descending
                                  else api.VRDX_CUDA_SORT_ORDER_ASCENDING)
         api.vrdxCudaCmdSortKeys64(self._stream(stream), self.handle, info, m,
