@@ -64,6 +64,67 @@ def ncu_traffic_per_launch(kind: str, n: int):
         return None
 
 
+def measure_dram_traffic_with_ncu(log2n: int, kv: bool, timeout_s: int = 300):
+    """DRAM bytes moved by ONE sort, per kernel, measured live on this box: tools/ncu_one.py (one sort of
+    resident data through the C-ABI) under `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`.
+    Traffic is a counter, not a time, so taking it under the profiler is legitimate; nothing timed comes
+    from this run.  Returns {"kernels": {name: bytes}, "whole_sort": bytes} or None."""
+    import csv
+    import io
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--csv",
+           sys.executable, os.path.join(ROOT, "tools", "ncu_one.py"), str(log2n), "kv" if kv else "keys", "1"]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, cwd=ROOT).stdout
+    except Exception:
+        return None
+    start = out.find('"ID"')
+    if start < 0:
+        return None
+    per_kernel, order = {}, []
+    for row in csv.DictReader(io.StringIO(out[start:])):
+        name = row.get("Kernel Name", "")
+        if not any(t in name for t in ("PassKernel", "Upsweep", "Spine", "Histogram", "StampStart", "CopyBack")):
+            continue   # torch's own kernels (the restore copy) are not part of the sort
+        try:
+            val = float(row["Metric Value"].replace(",", ""))
+        except (KeyError, ValueError):
+            continue
+        unit = row.get("Metric Unit", "byte").lower()
+        val *= {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
+        key = name.split("(")[0]
+        if key not in per_kernel:
+            order.append(key)
+        per_kernel[key] = per_kernel.get(key, 0.0) + val
+    if not per_kernel:
+        return None
+    return {"kernels": {k: per_kernel[k] for k in order}, "whole_sort": sum(per_kernel.values())}
+
+
+def probe_vulkan():
+    """Is there a Vulkan loader / NVIDIA ICD on this box?  (north_star: time the reference's Vulkan path
+    'if the driver exposes Vulkan'; SURVEY section 8c found none in the build container.)"""
+    import ctypes.util
+    import glob
+    import shutil
+    icds = sorted(glob.glob("/usr/share/vulkan/icd.d/*.json") + glob.glob("/etc/vulkan/icd.d/*.json"))
+    loader = ctypes.util.find_library("vulkan")
+    loaded = False
+    for cand in ([loader] if loader else []) + ["libvulkan.so.1"]:
+        try:
+            ctypes.CDLL(cand)
+            loaded = True
+            break
+        except OSError:
+            pass
+    return {"loader": loader, "loader_loads": loaded, "icd_files": icds, "vulkaninfo": shutil.which("vulkaninfo"),
+            "nvidia_icd": any("nvidia" in os.path.basename(p).lower() for p in icds),
+            "reference_vulkan_path": "n/a: no Vulkan loader/ICD on this box" if not (loaded and icds) else "loader and ICD present"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -137,23 +198,32 @@ def run_reference(args):
         kind = "port"
         def sort(k):
             t0 = time.perf_counter(); cpu_oracle.sort_keys(k); return time.perf_counter() - t0
-    # bounded sample: the whole run must end within minutes; std::sort does ~8.6 MKeys/s/core
-    budget_keys = 8.0e6 * 150.0 / max(1, steps + warmup)
-    log2s = max(18, min(25, int(np.floor(np.log2(budget_keys)))))
+    # Same config as our arm at N=1: the FULL 2^28-key workload per step (std::sort needs ~20-25 s for it, so
+    # the step count is capped internally to keep the whole run within a few minutes; ms_per_step is per
+    # full sort).  For N>1 (2^29 keys per GPU x N) the CPU arm sorts the same 2^28-key sample and says so.
+    log2s = args.log2n if args.log2n_reference is None else args.log2n_reference
     n = 1 << log2s
+    est_s = n * np.log2(n) / (2 ** 25 * 25 / 3.9)     # std::sort here: 2^25 keys in ~3.9 s, n log n scaling
+    warmup_done = min(warmup, 1 if est_s > 5 else warmup)
+    steps_done = max(1, min(steps, int(150.0 / max(est_s, 1e-3)) - warmup_done)) if est_s > 5 else steps
     keys = gen_keys(n)
-    for _ in range(warmup):
+    for _ in range(warmup_done):
         sort(keys)
-    times = [sort(keys) for _ in range(steps)]
+    times = [sort(keys) for _ in range(steps_done)]
     mean_s = sum(times) / len(times)
     value = n / mean_s / 1e9
-    sample = f"first 2^{log2s} keys of the 2^28-key workload per step; std::sort, 1 thread (the reference's CpuBenchmark is single-threaded)"
+    same = (args.gpus == 1 and log2s == 28)
+    sample = (f"the full 2^{log2s}-key workload per step ({steps_done} timed step(s), {warmup_done} warm-up: capped "
+              f"internally from --steps {steps} --warmup {warmup}); std::sort, 1 thread (the reference's CpuBenchmark::Sort "
+              f"is single-threaded, bench/cpu_benchmark.cc:19-28)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": warmup, "ms_per_step": mean_s * 1e3, "higher_is_better": True,
+        "steps": steps_done, "warmup": warmup_done, "ms_per_step": mean_s * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "32-bit keys-only, uniform (DataGenerator seed 1), CPU sample of 2^%d keys" % log2s,
-                   "host_cores": os.cpu_count()},
+        "config": {"workload": f"32-bit keys-only, N=2^{log2s} uniform random (DataGenerator seed 1), CpuBenchmark::Sort"
+                               + ("" if args.gpus == 1 else f" (CPU sample of the {args.gpus}-GPU workload: one 2^{log2s}-key slice)"),
+                   "same_config_as_our_arm": same, "host_cores": os.cpu_count(),
+                   "steps_requested": steps, "warmup_requested": warmup},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -215,6 +285,84 @@ def time_e2e(sorter, torch, host_keys, n, steps, warmup):
         if it >= warmup:
             ms.append(e0.elapsed_time(e1))
     return ms, pinned_out
+
+
+def time_e2e_kv(sorter, torch, host_keys, host_vals, n, steps, warmup):
+    """Key-value sort with HOST buffers: keys and values H2D + vrdxCmdSortKeyValue + both D2H, all timed."""
+    pin_k = torch.from_numpy(host_keys.view("int32")).pin_memory()
+    pin_v = torch.from_numpy(host_vals.view("int32")).pin_memory()
+    out_k = torch.empty(n, dtype=torch.int32).pin_memory()
+    out_v = torch.empty(n, dtype=torch.int32).pin_memory()
+    dk = torch.empty(n, dtype=torch.int32, device="cuda")
+    dv = torch.empty(n, dtype=torch.int32, device="cuda")
+    storage = sorter.storage_for(n, True)
+    ms = []
+    for it in range(warmup + steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dk.copy_(pin_k, non_blocking=True)
+        dv.copy_(pin_v, non_blocking=True)
+        sorter.sort_key_value(dk, dv, storage=storage)
+        out_k.copy_(dk, non_blocking=True)
+        out_v.copy_(dv, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= warmup:
+            ms.append(e0.elapsed_time(e1))
+    return sum(ms) / len(ms)
+
+
+def bench_config4(sorter, torch, api, cpu_oracle):
+    """BASELINE.json configs[3] / SURVEY 8(d) config 4: vrdxCmdSortIndirect and ...KeyValueIndirect with the count
+    in device memory, maxElementCount = 2^27, n = 2^27 - 4099 (odd, no multiple of any tile size), keys skewed
+    (AND of three draws) / 8-bit / all-equal.  Resident data, CUDA events, median of 5 after 2 warm-ups; every
+    result is checked (sorted + multiset; key-value: values = index, so stability is visible) and the
+    [n, max) tail of the caller's buffers must be untouched."""
+    import numpy as np
+    from vulkan_radix_sort_b200.datagen import make_keys
+    nmax = 1 << 27
+    n = nmax - 4099
+    out = {"max_element_count": nmax, "element_count": n}
+    count = torch.tensor([n], dtype=torch.int32, device="cuda")
+    idx = torch.arange(nmax, dtype=torch.int32, device="cuda")
+    for dist_name in ("skewed", "bits8", "all_zero"):
+        host = make_keys(dist_name, nmax, 1)
+        host[n:] = 0xDEADBEEF                      # tail marker: must survive every sort
+        src = torch.from_numpy(host.view(np.int32)).cuda()
+        for kv in (False, True):
+            keys = torch.empty_like(src)
+            vals = torch.empty_like(src) if kv else None
+            storage = sorter.storage_for(nmax, kv)
+            ms = []
+            for it in range(7):
+                keys.copy_(src)
+                if kv:
+                    vals.copy_(idx)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                if kv:
+                    sorter.sort_key_value_indirect(keys, vals, count, max_count=nmax, storage=storage)
+                else:
+                    sorter.sort_indirect(keys, count, max_count=nmax, storage=storage)
+                e1.record()
+                torch.cuda.synchronize()
+                if it >= 2:
+                    ms.append(e0.elapsed_time(e1))
+            k = keys.cpu().numpy().view(np.uint32)
+            ok = cpu_oracle.is_sorted(k[:n]) and bool((k[n:] == 0xDEADBEEF).all()) and \
+                cpu_oracle.multiset_fingerprint(k[:n]) == cpu_oracle.multiset_fingerprint(host[:n])
+            if kv:
+                v = vals.cpu().numpy().view(np.uint32)
+                ok = ok and cpu_oracle.check_stable_permutation(host[:n], k[:n], v[:n]) and \
+                    bool((v[n:] == np.arange(n, nmax, dtype=np.uint32)).all())
+            med = statistics.median(ms)
+            out[f"{dist_name}_{'key_value' if kv else 'keys_only'}"] = {
+                "value": n / (med * 1e-3) / 1e9, "unit": UNIT, "ms_per_step_median": med, "verified": bool(ok)}
+            del keys, vals
+        del src
+    return out
 
 
 def time_e2e_pipelined(sorter, torch, host_keys, n, steps, warmup):
@@ -301,15 +449,29 @@ def run_single(args):
     assert all(cpu_oracle.is_sorted(o.numpy().view(np.uint32)) for o in pipe_out)
     del pipe_out
 
-    # roofline of the dominant kernel (one onesweep pass): algorithmic 8 B/key per launch
+    # roofline of the dominant kernel (the scatter pass of one LSD pass): algorithmic 8 B/key per launch.
+    # traffic = DRAM bytes measured live by ncu on this box, for that kernel (per launch) AND for the whole
+    # sort (reduce-then-scan re-reads the keys once per pass: ~48 B/key moved vs 36 algorithmic).
     pass_gbs = PASS_BYTES_PER_KEY_KEYS * n / (pass_ms * 1e-3) / 1e9
+    traffic = None if args.no_ncu else measure_dram_traffic_with_ncu(log2n, False)
+    pass_traffic, traffic_src = ncu_traffic_per_launch("keys_pass", n), "committed capture (profiles/ncu_traffic.json)"
+    whole_traffic = None
+    if traffic:
+        pk = [v for k, v in traffic["kernels"].items() if "PassKernel" in k]
+        if pk:
+            pass_traffic, traffic_src = sum(pk) / 4.0, "measured in this run (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum)"
+        whole_traffic = traffic["whole_sort"]
     roofline = {"bound": "hbm", "achieved": pass_gbs, "peak": peak, "unit": "GB/s", "frac": pass_gbs / peak,
-                "traffic": ncu_traffic_per_launch("keys_pass", n), "kernel": "OnesweepKernel<.., MODE 1> (scatter pass of one LSD pass, keys-only)",
+                "traffic": pass_traffic, "traffic_source": traffic_src,
+                "kernel": "PassKernel<.., MODE 1> (scatter pass of one LSD pass, keys-only; mean of the 4 passes)",
                 "algorithmic_bytes_per_launch": PASS_BYTES_PER_KEY_KEYS * n, "kernel_ms": pass_ms,
                 "peak_source": peak_src,
                 "whole_sort": {"bytes_per_key": BYTES_PER_KEY_KEYS,
                                "achieved": BYTES_PER_KEY_KEYS * n / (ms_per_step * 1e-3) / 1e9,
-                               "frac": BYTES_PER_KEY_KEYS * n / (ms_per_step * 1e-3) / 1e9 / peak}}
+                               "frac": BYTES_PER_KEY_KEYS * n / (ms_per_step * 1e-3) / 1e9 / peak,
+                               "traffic": whole_traffic,
+                               "traffic_over_algorithmic": (whole_traffic / (BYTES_PER_KEY_KEYS * n)) if whole_traffic else None,
+                               "traffic_by_kernel": traffic["kernels"] if traffic else None}}
 
     # extras: key-value at the same N, and both kinds at 2^25 (parity-test sizes, reported for the record)
     extra = {"e2e_pipelined_batches": {
@@ -341,6 +503,38 @@ def run_single(args):
                     "note": "3.4e7-key working set fits in the 126 MB L2 in part; restore copy between steps"}
     except torch.cuda.OutOfMemoryError as e:  # pragma: no cover
         extra["error"] = str(e)
+
+    # BASELINE.json configs[3]: indirect sort (device-resident count), adversarial keys, non-power-of-two N
+    try:
+        extra["config4_indirect_adversarial"] = bench_config4(sorter, torch, api, cpu_oracle)
+    except Exception as e:  # pragma: no cover
+        extra["config4_error"] = repr(e)
+    # key-value end to end (host buffers, copies inside the timed region)
+    try:
+        host_vals = gen_keys(n, seed=2)
+        kv_e2e_ms = time_e2e_kv(sorter, torch, host_keys, host_vals, n, 3, 2)
+        extra["key_value_e2e_2^%d" % log2n] = {"value": n / (kv_e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": kv_e2e_ms,
+                                               "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n}
+        del host_vals
+    except Exception as e:  # pragma: no cover
+        extra["key_value_e2e_error"] = repr(e)
+    # the reference's own bench protocol with the b200 backend (bench/benchmark_factory.cc:14-25): one point
+    try:
+        exe = os.path.join(ROOT, "bench_cpp", "bench")
+        if os.path.exists(exe):
+            torch.cuda.empty_cache()
+            out = subprocess.run([exe, "b200", "--sizes", "2^25", "--seed", "1", "--runs", "5", "-o", "/tmp/vrdx_b200.csv"],
+                                 capture_output=True, text=True, timeout=240)
+            passed = "Correctness check passed" in out.stdout
+            for ln in open("/tmp/vrdx_b200.csv"):
+                f = ln.strip().split(",")
+                if len(f) == 7 and f[0] == "b200":
+                    extra["bench_cpp_b200_%s_2^25" % ("keys_only" if f[2] == "keys" else "key_value")] = {
+                        "value": float(f[5]), "unit": UNIT, "gpu_ms": float(f[3]), "correctness_check_passed": passed,
+                        "note": "bench_cpp/bench b200 (the reference's CLI, protocol and CSV schema; fresh data per run, median of 5)"}
+    except Exception as e:  # pragma: no cover
+        extra["bench_cpp_error"] = repr(e)
+    extra["vulkan_probe"] = probe_vulkan()
 
     # comparison point named by BASELINE.json: CUB Onesweep on the same box, through the reference's
     # bench protocol (bench_cpp/bench cuda).  Comparison only — CUB is not in libvrdx_b200.so.
@@ -383,7 +577,7 @@ def run_single(args):
                    "l2": "inputs (1 GiB) larger than L2; a restore copy of the unsorted keys runs between timed steps",
                    "timing": "CUDA events on the launching stream around each sort; mean of K steps",
                    "algorithm": "AUTO: reduce-then-scan at this N (per pass: chunked upsweep, 2 spine kernels, "
-                                "look-back-free scatter), 8-bit digits x 4 passes; onesweep below 3*2^23 keys"},
+                                "look-back-free scatter), 8-bit digits x 4 passes; onesweep below the measured crossover"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_per_step,
                 "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": 4 * n,
                 "path": "pinned host keys -> cudaMemcpyAsync H2D -> vrdxCmdSort (C-ABI) -> cudaMemcpyAsync D2H"},
@@ -410,8 +604,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=28, help="developer override of the N=1 workload size")
+    ap.add_argument("--log2n-reference", type=int, default=None,
+                    help="developer override of the --impl reference size (default: the N=1 workload, 2^28)")
     ap.add_argument("--log2n-per-gpu", type=int, default=29, help="developer override of the N>1 per-GPU size")
+    ap.add_argument("--log2n-adversarial", type=int, default=24,
+                    help="N>1: keys per GPU of the untimed adversarial parity sorts (all_zero, skewed, bits4, all_ones)")
     ap.add_argument("--no-cub", action="store_true", help="skip the CUB comparison run")
+    ap.add_argument("--no-ncu", action="store_true", help="skip the live ncu DRAM-traffic measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -12,7 +12,11 @@
 //          reference uses (bench/cuda_benchmark.cu:48-63, 94-111).  Comparison only: CUB is linked
 //          into THIS binary, never into libvrdx_b200.so.
 //   cpu    std::sort / std::stable_sort on indices + gather (bench/cpu_benchmark.cc:19-53).
-// Written from scratch; cxxopts (a network fetch in the reference) is replaced by hand parsing.
+// Inputs and verifier: where the reference tree is present at build time (this container), the binary
+// is built against the reference's OWN bench/data_generator.cc and bench/cpu_benchmark.cc, compiled
+// where they lie (north_star: the b200 backend "reuses data_generator and the existing verifier");
+// without it (make REFERENCE=) the in-file mirrors below are used.  `bench --help` says which.
+// cxxopts (a network fetch in the reference) is replaced by hand parsing.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -36,8 +40,23 @@
 #include "vk_radix_sort.h"
 #include "vrdx_cuda.h"
 
+#ifdef VRDX_BENCH_REFERENCE_SOURCES
+#include "benchmark_base.h"   // /root/reference/bench (read where it lies, never copied)
+#include "cpu_benchmark.h"
+#include "data_generator.h"
+using Results = BenchmarkBase::Results;
+static const char* kInputsAndVerifier = "reference bench/data_generator.cc + bench/cpu_benchmark.cc (compiled unmodified)";
+#else
+static const char* kInputsAndVerifier = "in-file mirrors of bench/data_generator.cc and bench/cpu_benchmark.cc";
+#endif
+
 namespace {
 
+uint64_t NowNs() {
+  return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+#ifndef VRDX_BENCH_REFERENCE_SOURCES
 // ---------------------------------------------------------------------------- inputs
 // Same stream as the reference's DataGenerator (bench/data_generator.cc:12-27).
 struct SortData {
@@ -75,10 +94,6 @@ class BenchmarkBase {
   virtual Results SortKeyValue(const std::vector<uint32_t>& keys, const std::vector<uint32_t>& values) = 0;
 };
 
-uint64_t NowNs() {
-  return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
-}
-
 class CpuBenchmark : public BenchmarkBase {
  public:
   Results Sort(const std::vector<uint32_t>& keys) override {
@@ -106,6 +121,8 @@ class CpuBenchmark : public BenchmarkBase {
     return r;
   }
 };
+
+#endif  // !VRDX_BENCH_REFERENCE_SOURCES
 
 #define CK(x)                                                                               \
   do {                                                                                      \
@@ -341,7 +358,8 @@ void Usage() {
   std::cout << "Usage: bench <type> [-o results.csv] [--no-verify] [--sizes a,b,...] [--seed s] [--runs k]\n\n"
                "Types:\n  b200      B200-native CUDA backend of the vrdx API (this repo)\n"
                "  cuda      CUB Onesweep (CUDA)\n  cpu       std::sort reference\n\n"
-               "Without --sizes the reference sweep is run: N = 2^18 .. 2^25 in 128 linear steps.\n";
+               "Without --sizes the reference sweep is run: N = 2^18 .. 2^25 in 128 linear steps.\n"
+               "Inputs and verifier: " << kInputsAndVerifier << "\n";
 }
 
 }  // namespace

@@ -41,3 +41,38 @@ def test_cpu_backend_writes_the_reference_csv_schema(bench_exe, tmp_path):
     assert [(r[0], r[1], r[2]) for r in body] == [("cpu", "4096", "keys"), ("cpu", "4096", "kv"),
                                                    ("cpu", "5000", "keys"), ("cpu", "5000", "kv")]
     assert all(float(r[3]) > 0 and float(r[5]) > 0 for r in body)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("backend", ["b200", "cuda"])
+def test_gpu_backends_pass_the_reference_correctness_gate(bench_exe, tmp_path, backend):
+    """`bench b200` (and the CUB comparison backend) through the reference's own protocol —
+    the single correctness gate of bench/bench.cc:41-64,164-166 ("GPU == CpuBenchmark at N = 2^18"), the
+    factory line bench/benchmark_factory.cc:14-25, the stdout chain and the CSV schema, incl. the
+    up / sp / dn split VulkanBenchmark derives from the 15 timestamps (bench/vulkan_benchmark.cc:330-337)."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    path = tmp_path / f"{backend}.csv"
+    out = subprocess.run([bench_exe, backend, "--sizes", "2^18,262143,2^22", "--seed", "1", "--runs", "3", "-o", str(path)],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "Correctness check passed" in out.stdout
+    lines = open(path).read().splitlines()
+    assert lines[0].startswith("# version:")                               # bench.cc:193-197 (tools/plot.py skips '#')
+    rows = list(csv.reader(ln for ln in lines if not ln.startswith("#")))
+    assert rows[0] == ["backend", "n", "sort", "gpu_ms", "cpu_ms", "gpu_gitems_s", "cpu_gitems_s"]
+    body = rows[1:]
+    assert [(r[0], r[1], r[2]) for r in body] == [(backend, n, k) for n in ("262144", "262143", "4194304") for k in ("keys", "kv")]
+    assert all(float(r[3]) > 0 and float(r[4]) > 0 and float(r[5]) > 0 for r in body)
+    if backend == "b200":
+        # the per-stage split only exists for backends with timestamps; large N runs reduce-then-scan,
+        # where upsweep, spine and downsweep are separate kernels and all three columns are non-zero
+        big = subprocess.run([bench_exe, "b200", "--sizes", "2^26", "--seed", "1", "--runs", "2", "--no-verify",
+                              "-o", str(tmp_path / "big.csv")], capture_output=True, text=True, timeout=300)
+        assert big.returncode == 0, big.stdout + big.stderr
+        line = [ln for ln in big.stdout.splitlines() if "[keys]" in ln][0]
+        import re
+        m = re.search(r"\[up=([0-9.]+)ms\(\d+%\) sp=([0-9.]+)ms\(\d+%\) dn=([0-9.]+)ms\(\d+%\)\]", line)   # bench.cc:178-186
+        assert m, line
+        assert all(float(x) > 0 for x in m.groups()), line

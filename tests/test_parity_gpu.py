@@ -390,12 +390,15 @@ def test_full_size_uniform_keys_and_pairs(sorter, oracle, log2n):
     _property_check(oracle, k, to_np(dk), to_np(dv))
 
 
-@pytest.mark.parametrize("dist", ["skewed", "bits8", "bits4", "all_zero", "all_ones", "sorted", "reverse"])
-def test_indirect_adversarial_non_power_of_two(sorter, oracle, dist):
-    # BASELINE.json configs[3]: max = 2^27, device count = 2^27 - 4099
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("dist", ["skewed", "bits8", "bits4", "all_zero", "all_ones", "sorted", "reverse", "sentinel_mix"])
+def test_indirect_adversarial_non_power_of_two(sorter, oracle, dist, seed):
+    # BASELINE.json configs[3] / SURVEY 8(d) config 4: max = 2^27, device count = 2^27 - 4099, seeds {1, 2, 3}
+    if seed > 1 and dist in ("all_zero", "all_ones"):
+        pytest.skip("constant input: the seed does not change it")
     mx = 1 << 27
     n = mx - 4099
-    k = make_keys(dist, mx, seed=1)
+    k = make_keys(dist, mx, seed=seed)
     cnt = torch.tensor([n], dtype=torch.int32, device=DEV)
     dk = to_dev(k)
     dv = torch.arange(mx, dtype=torch.int32, device=DEV)
@@ -411,3 +414,71 @@ def test_indirect_adversarial_non_power_of_two(sorter, oracle, dist):
     torch.cuda.synchronize()
     out = to_np(dk)
     assert np.array_equal(out[:n], ok[:n]) and np.array_equal(out[n:], k[n:])
+
+
+def test_two_host_threads_share_one_sorter(sorter, oracle):
+    """SURVEY 8(b) threading row: the sorter is immutable after creation, so two host threads may record
+    into different command buffers (streams) with different storage at the same time."""
+    import threading
+    n = 1 << 20
+    inputs = [DataGenerator(100 + t).generate(n) for t in range(2)]
+    results, errors = [None, None], []
+
+    def work(t):
+        try:
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                storage = torch.empty(sorter.storage_requirements(n, True).size, dtype=torch.uint8, device=DEV)
+                for rep in range(8):
+                    dk, dv = to_dev(inputs[t][0]), to_dev(inputs[t][1])
+                    sorter.sort_key_value(dk, dv, storage=storage, stream=stream)
+                stream.synchronize()
+                results[t] = (to_np(dk), to_np(dv))
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(2)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for t in range(2):
+        ek, ev = oracle.sort_key_value(*inputs[t])
+        assert np.array_equal(results[t][0], ek) and np.array_equal(results[t][1], ev)
+
+
+def test_one_process_drives_two_devices(oracle):
+    """Kernel attributes (> 48 KB dynamic shared memory) are per device: a second sorter on another GPU of the
+    same process must prepare that GPU too (round-1 ADVICE, vrdx_api.cu `static prepared`)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    from vulkan_radix_sort_b200 import Sorter
+    n = (1 << 22) + 77          # large enough for the 128 KB lane-private histogram kernel
+    outs = []
+    sorters = [Sorter(d) for d in (0, 1)]
+    k, v = DataGenerator(5).generate(n)
+    for d, s in enumerate(sorters):
+        with torch.cuda.device(d):
+            dk = torch.from_numpy(k.view(np.int32)).to(f"cuda:{d}")
+            dv = torch.from_numpy(v.view(np.int32)).to(f"cuda:{d}")
+            s.sort_key_value(dk, dv)
+            torch.cuda.synchronize(d)
+            outs.append((dk.cpu().numpy().view(np.uint32), dv.cpu().numpy().view(np.uint32)))
+            # the multi-GPU histogram kernel with its largest shared-memory footprint (12 bits x 4 prefixes = 64 KB)
+            hist = torch.zeros(4 << 12, dtype=torch.int32, device=f"cuda:{d}")
+            pref = torch.arange(4, dtype=torch.int32, device=f"cuda:{d}")
+            api.load_library().vrdxDistCmdPrefixHistogram(torch.cuda.current_stream(d).cuda_stream, s.handle, n,
+                                                          dk.data_ptr(), 0, 8, 12, 4, pref.data_ptr(), 0, hist.data_ptr(), 0)
+            s.check()
+            torch.cuda.synchronize(d)
+            got = hist.cpu().numpy().astype(np.int64).reshape(4, 1 << 12)
+            ks = np.sort(k)
+            for p in range(4):
+                sel = ks[(ks >> 20) == p]
+                assert np.array_equal(got[p], np.bincount((sel >> 8) & 0xFFF, minlength=1 << 12)), (d, p)
+    ek, ev = oracle.sort_key_value(k, v)
+    for ok_, ov_ in outs:
+        assert np.array_equal(ok_, ek) and np.array_equal(ov_, ev)
+    for s in sorters:
+        s.close()

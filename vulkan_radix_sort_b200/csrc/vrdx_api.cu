@@ -105,7 +105,7 @@ static const TileShape kPairShapes[] = {
     MakeShape<384, 16, true, 3>(), MakeShape<256, 16, true, 5>(), MakeShape<256, 16, true, 4>(),
     MakeShape<256, 16, true, 3>(), MakeShape<512, 16, true, 2>(),
 };
-constexpr int kDefaultKeysRtsShape = 1;
+constexpr int kDefaultKeysRtsShape = 2;  // 256 x 16, 4 CTAs/SM: 64 registers, no spills (profiles/r02/b_relaxed_on.txt)
 constexpr int kDefaultPairRtsShape = 0;
 constexpr int kDefaultOnesweepShape = 0;  // keys and pairs
 constexpr int kNumKeysShapes = sizeof(kKeysShapes) / sizeof(kKeysShapes[0]);
@@ -132,7 +132,9 @@ struct VrdxSorter_T {
   VrdxCudaTileLoad tile_load = VRDX_CUDA_TILE_LOAD_AUTO;
   int keys_shape = kDefaultOnesweepShape, pair_shape = kDefaultOnesweepShape;        // onesweep
   int keys_rts_shape = kDefaultKeysRtsShape, pair_rts_shape = kDefaultPairRtsShape;  // reduce-then-scan
+  int keys_rts_ctas = 1, pair_rts_ctas = 1;               // co-resident CTAs per SM of the scatter kernels
   bool pdl = true;                                        // programmatic dependent launch between our own kernels
+  bool relaxed_equal_low_bits = true;                     // PassArgs::words_only (developer switch VRDX_RELAXED=0)
   uint32_t hist_private_min_count = kHistPrivateMinCount;  // lane-private histogram bins from this count up
 #ifdef VRDX_EXPERIMENTS
   ExperimentSelection exp;
@@ -145,6 +147,19 @@ struct VrdxSorter_T {
 // A VkQueryPool on this backend: device memory the sort's own kernels stamp with %globaltimer
 // (like vkCmdWriteTimestamp, the write happens on the GPU timeline and costs no stream
 // serialisation).  Slots that coincide (no kernel between them) alias an earlier slot.
+// Storage layout of a sorter: 32-bit look-back rows only for the counts it may sort with onesweep.
+static StorageLayout SorterLayout(const VrdxSorter_T* s, uint64_t max_count, bool key_value) {
+#ifdef VRDX_EXPERIMENTS
+  return ComputeLayout(max_count, kMinTile, ~0ull, true);  // the round-1 kernels keep 32-bit per-tile rows everywhere
+#else
+  // (a NULL sorter — legal for the pure size query — is answered like the default, AUTO, sorter)
+  if (s && s->algorithm == VRDX_CUDA_ALGORITHM_ONESWEEP) return ComputeLayout(max_count, kMinTile, ~0ull);
+  if (s && s->algorithm == VRDX_CUDA_ALGORITHM_REDUCE_THEN_SCAN) return ComputeLayout(max_count, kMinTile, 0);
+  // AUTO: a count below the crossover of this kind of sort may run onesweep
+  return ComputeLayout(max_count, kMinTile, key_value ? kAutoRtsThresholdPairs : kAutoRtsThresholdKeys);
+#endif
+}
+
 struct VrdxQueryPool_T {
   int device = 0;
   uint32_t count = 0;
@@ -301,7 +316,7 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
                        (sorter->algorithm == VRDX_CUDA_ALGORITHM_AUTO &&
                         n_or_max >= (kv ? kAutoRtsThresholdPairs : kAutoRtsThresholdKeys));
 
-  const StorageLayout lay = ComputeLayout(n_or_max, kMinTile);
+  const StorageLayout lay = SorterLayout(sorter, n_or_max, kv);
   StorageHeader* hdr = reinterpret_cast<StorageHeader*>(storage + lay.header_offset);
   uint32_t* status[2] = {reinterpret_cast<uint32_t*>(storage + lay.status_a_offset),
                          reinterpret_cast<uint32_t*>(storage + lay.status_b_offset)};
@@ -319,8 +334,9 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
   // Key types, order and bit sub-ranges run the GENERIC instantiation of the same tile kernel.
   const bool generic = !plan.reference;
   const bool pdl = sorter->pdl;
-  const TileShape& shape = use_rts ? (kv ? kPairShapes[sorter->pair_rts_shape] : kKeysShapes[sorter->keys_rts_shape])
-                                   : (kv ? kPairShapes[sorter->pair_shape] : kKeysShapes[sorter->keys_shape]);
+  const TileShape* chosen = use_rts ? (kv ? &kPairShapes[sorter->pair_rts_shape] : &kKeysShapes[sorter->keys_rts_shape])
+                                    : (kv ? &kPairShapes[sorter->pair_shape] : &kKeysShapes[sorter->keys_shape]);
+  const TileShape& shape = *chosen;
   uint32_t tile_size = shape.tile;
 #ifdef VRDX_EXPERIMENTS
   const ExperimentKernel* ek = generic ? nullptr : PickExperiment(sorter->exp, kv, keys, values, storage);
@@ -328,6 +344,18 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
 #endif
   const uint32_t tiles = (uint32_t)CeilDiv(n_or_max, tile_size);
   uint32_t pass_grid = tiles;
+#ifdef VRDX_EXPERIMENTS
+  // experiment: reduce-then-scan over ranges of consecutive tiles (RangePassKernel), tables sized by a constant
+  const bool persistent = use_rts && ek && ek->range_tiles != 0;
+  uint32_t range_tiles = 1, ranges = tiles;
+  if (persistent) {
+    range_tiles = ek->range_tiles > 0 ? (uint32_t)ek->range_tiles   // fixed range length, capped at kMaxRanges rows
+                                      : (uint32_t)CeilDiv(tiles, (uint64_t)sorter->sm_count * (uint64_t)*ek->ctas_per_sm);
+    const uint32_t floor_tiles = (uint32_t)CeilDiv(tiles, (uint64_t)kMaxRanges);
+    if (range_tiles < floor_tiles) range_tiles = floor_tiles;
+    ranges = (uint32_t)CeilDiv(tiles, (uint64_t)range_tiles);
+  }
+#endif
 #ifdef VRDX_EXPERIMENTS
   if (ek) pass_grid = ExperimentGrid(*ek, tiles, use_rts, sorter->sm_count);
 #endif
@@ -368,6 +396,10 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
     if (pass == 0) args.codec_in = plan.digits.codec;
     if (pass + 1 == passes) args.codec_out = plan.digits.codec;
     args.order_free = (!kv && pass == 0 && plan.all_bits) ? 1u : 0u;
+#ifdef VRDX_EXPERIMENTS
+    args.range_tiles = range_tiles;
+#endif
+    args.words_only = (!kv && plan.all_bits && sorter->relaxed_equal_low_bits) ? 1u : 0u;
     args.hdr = hdr;
     args.status = status[pass & 1];
     args.status_next = (pass + 1 < passes) ? status[(pass + 1) & 1] : nullptr;
@@ -377,10 +409,30 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
     args.vals_in = kv ? ((pass & 1) ? vals_alt : values) : nullptr;
     args.vals_out = kv ? ((pass & 1) ? values : vals_alt) : nullptr;
 
+#ifdef VRDX_EXPERIMENTS
+    if (use_rts && persistent) {
+      // The reference's three stages with tables sized by the machine: `ranges` co-resident CTAs, CTA r owns a
+      // contiguous tile range; table A = one digit-count row per range -> exclusive prefixes (spine), the
+      // spine's segment sums live in the rows after them.  Timestamps fall where the reference puts them.
+      args.status = status[0];
+      args.status_next = nullptr;
+      args.ts_end = st.Written(2 + 3 * pass + 0);
+      NoteError(sorter, ek->launch_upsweep(stream, ranges, args, pdl));
+      uint32_t* seg = status[0] + (size_t)ranges * kRadix;
+      const uint32_t seg_grid = ranges < (uint32_t)kSpineSegments ? ranges : (uint32_t)kSpineSegments;
+      NoteError(sorter, LaunchEx(SpineReduceKernel, seg_grid, (uint32_t)kRadix, 0, stream, pdl, indirect, n_or_max,
+                                 tile_size, ranges, pass, (const uint32_t*)status[0], seg, hdr));
+      NoteError(sorter, LaunchEx(SpineApplyKernel, seg_grid, (uint32_t)kRadix, 0, stream, pdl, indirect, n_or_max,
+                                 tile_size, ranges, status[0], (const uint32_t*)seg, st.Written(2 + 3 * pass + 1)));
+      args.ts_end = st.Written(2 + 3 * pass + 2);
+      NoteError(sorter, ek->launch(stream, ranges, args, 1, pdl));
+      launches += 4;
+      continue;
+    }
+#endif
     if (use_rts) {
-      // the reference's three stages: status A = per-tile digit prefixes inside a chunk of kSpineChunk
-      // tiles, status B = spine chunk sums -> exclusive prefixes; timestamps fall exactly where the
-      // reference puts them
+      // the reference's three stages: table A = per-tile digit prefixes inside a chunk of kSpineChunk tiles
+      // (16-bit), table B = spine chunk sums -> exclusive prefixes; timestamps fall where the reference puts them
       args.status = status[0];
       args.status_next = status[1];
       const uint32_t chunks = (uint32_t)CeilDiv(tiles, (uint64_t)kSpineChunk);
@@ -394,9 +446,9 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
       uint32_t* seg = status[1] + (size_t)chunks * kRadix;
       const uint32_t seg_grid = chunks < (uint32_t)kSpineSegments ? (chunks ? chunks : 1u) : (uint32_t)kSpineSegments;
       NoteError(sorter, LaunchEx(SpineReduceKernel, seg_grid, (uint32_t)kRadix, 0, stream, pdl, indirect,
-                                 n_or_max, tile_size, pass, (const uint32_t*)status[1], seg, hdr));
+                                 n_or_max, tile_size, 0u, pass, (const uint32_t*)status[1], seg, hdr));
       NoteError(sorter, LaunchEx(SpineApplyKernel, seg_grid, (uint32_t)kRadix, 0, stream, pdl, indirect,
-                                 n_or_max, tile_size, status[1], (const uint32_t*)seg,
+                                 n_or_max, tile_size, 0u, status[1], (const uint32_t*)seg,
                                  st.Written(2 + 3 * pass + 1)));
       args.ts_end = st.Written(2 + 3 * pass + 2);
 #ifdef VRDX_EXPERIMENTS
@@ -486,14 +538,14 @@ VkResult vrdxCudaCreateSorter(const VrdxSorterCreateInfo* pCreateInfo,
   // "Pipeline creation" (h.in:141-262): opt every kernel this sorter can launch into its shared-memory
   // footprint.  cudaFuncSetAttribute applies to the CURRENT device, so this runs for every sorter, under
   // the device guard above: a process that drives several GPUs prepares each of them.
-  int unused = 0;
+  int unused = 0, keys_rts_ctas = 0, pair_rts_ctas = 0;
   if (kKeysShapes[kDefaultOnesweepShape].prepare(&unused) != cudaSuccess ||  // vrdxCudaCmdSortEx runs the defaults too
       kPairShapes[kDefaultOnesweepShape].prepare(&unused) != cudaSuccess ||
       kKeysShapes[kDefaultKeysRtsShape].prepare(&unused) != cudaSuccess ||
       kPairShapes[kDefaultPairRtsShape].prepare(&unused) != cudaSuccess ||
       kKeysShapes[keys_shape].prepare(&unused) != cudaSuccess || kPairShapes[pair_shape].prepare(&unused) != cudaSuccess ||
-      kKeysShapes[keys_rts_shape].prepare(&unused) != cudaSuccess ||
-      kPairShapes[pair_rts_shape].prepare(&unused) != cudaSuccess ||
+      kKeysShapes[keys_rts_shape].prepare(&keys_rts_ctas) != cudaSuccess ||
+      kPairShapes[pair_rts_shape].prepare(&pair_rts_ctas) != cudaSuccess || keys_rts_ctas < 1 || pair_rts_ctas < 1 ||
       cudaFuncSetAttribute(HistogramKernelPrivate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)kHistPrivSmemBytes) != cudaSuccess ||
       cudaFuncSetAttribute(HistogramKernelPrivate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -514,8 +566,11 @@ VkResult vrdxCudaCreateSorter(const VrdxSorterCreateInfo* pCreateInfo,
   s->keys_rts_shape = keys_rts_shape;
   s->pair_rts_shape = pair_rts_shape;
   s->tile_load = tile_load;
+  s->keys_rts_ctas = keys_rts_ctas;
+  s->pair_rts_ctas = pair_rts_ctas;
   if (const char* e = getenv("VRDX_ALGORITHM")) s->algorithm = (VrdxCudaAlgorithm)atoi(e);
   if (const char* e = getenv("VRDX_PDL")) s->pdl = atoi(e) != 0;
+  if (const char* e = getenv("VRDX_RELAXED")) s->relaxed_equal_low_bits = atoi(e) != 0;
   if (const char* e = getenv("VRDX_HIST_PRIVATE_MIN")) s->hist_private_min_count = (uint32_t)strtoul(e, nullptr, 10);
 #ifdef VRDX_EXPERIMENTS
   if (!PrepareExperiments(&s->exp, experiment, tile_load, s->sm_count)) {
@@ -540,18 +595,18 @@ void vrdxDestroySorter(VrdxSorter sorter) {
   delete sorter;
 }
 
-void vrdxGetSorterStorageRequirements(VrdxSorter /*sorter*/, uint32_t maxElementCount,
+void vrdxGetSorterStorageRequirements(VrdxSorter sorter, uint32_t maxElementCount,
                                       VrdxSorterStorageRequirements* requirements) {
   if (!requirements) return;
-  const StorageLayout lay = ComputeLayout(maxElementCount, kMinTile);
+  const StorageLayout lay = SorterLayout(sorter, maxElementCount, false);
   requirements->size = lay.total_keys;
   requirements->usage = VK_BUFFER_USAGE_STORAGE_BUFFER_BIT | VK_BUFFER_USAGE_TRANSFER_DST_BIT;
 }
 
-void vrdxGetSorterKeyValueStorageRequirements(VrdxSorter /*sorter*/, uint32_t maxElementCount,
+void vrdxGetSorterKeyValueStorageRequirements(VrdxSorter sorter, uint32_t maxElementCount,
                                               VrdxSorterStorageRequirements* requirements) {
   if (!requirements) return;
-  const StorageLayout lay = ComputeLayout(maxElementCount, kMinTile);
+  const StorageLayout lay = SorterLayout(sorter, maxElementCount, true);
   requirements->size = lay.total_kv;
   requirements->usage = VK_BUFFER_USAGE_STORAGE_BUFFER_BIT | VK_BUFFER_USAGE_TRANSFER_DST_BIT;
 }
@@ -745,10 +800,10 @@ void vrdxCudaReleaseImportedMemory(VrdxCudaImportedMemory memory) {
   delete memory;
 }
 
-void vrdxCudaGetSorterKeys64StorageRequirements(VrdxSorter /*sorter*/, uint32_t maxElementCount,
+void vrdxCudaGetSorterKeys64StorageRequirements(VrdxSorter sorter, uint32_t maxElementCount,
                                                 VrdxSorterStorageRequirements* requirements) {
   if (!requirements) return;
-  const StorageLayout lay = ComputeLayout(maxElementCount, kMinTile);
+  const StorageLayout lay = SorterLayout(sorter, maxElementCount, true);
   // lo[] | hi[] | storage of a key-value sort
   requirements->size = 2 * AlignUp((uint64_t)maxElementCount * sizeof(uint32_t), (uint64_t)kOffsetAlignment) + lay.total_kv;
   requirements->usage = VK_BUFFER_USAGE_STORAGE_BUFFER_BIT | VK_BUFFER_USAGE_TRANSFER_DST_BIT;

@@ -7,6 +7,8 @@
 //                          repair loop); MODE 2 = tile id from blockIdx.x; PAIRED 64-bit staging
 //   OnesweepClusterKernel  one decoupled look-back per thread-block cluster (DSMEM)
 //   OnesweepTmaKernel      persistent CTAs, cp.async.bulk (TMA) double-buffered tile staging
+//   RangePassKernel        reduce-then-scan whose tables are sized by the machine / a constant instead of by N:
+//                          a CTA walks a RANGE of consecutive tiles with running digit offsets (round 2)
 #pragma once
 #include <cooperative_groups.h>
 
@@ -756,5 +758,194 @@ OnesweepTmaKernel(const PassArgs a) {
   }
   StampEnd(a.ts_end);
 }
+
+// ------------------------------------------------------------------------------------------
+// RangePassKernel — the scatter pass of reduce-then-scan with tables sized by a CONSTANT, not
+// by N (north_star: "a temp-storage layout sized for 148 SMs"; the reference keeps one 1 KB
+// row per 4096 keys, h.in:353-362).
+//
+// CTA r owns the `range_tiles` consecutive tiles of range r.  UpsweepRangeKernel counted the
+// range's digits into ONE row range_counts[r][256], the spine turned the rows into exclusive
+// prefixes, and this kernel walks the range tile by tile with a running per-digit offset in a
+// register of the digit thread: a tile's own digit counts fall out of its ranking anyway, so
+// no per-tile table exists.  The number of ranges is capped at kMaxRanges rows (the host grows
+// range_tiles with N), so the tables take at most 8.4 MB for any N <= 2^32 - 1 where the
+// reference's partHist takes N / 16 bytes (64 MB at 2^28).  Two more things the loop buys: the keys
+// of the next tile are requested as soon as the current tile sits in shared memory (their
+// latency hides behind the scatter), and every warp re-zeroes only its own counter row (no
+// block barrier for it).
+// Why ranges of 8..32 tiles and not ONE range per co-resident CTA (148 x 5 = 740 rows): measured
+// (profiles/r02/b_persistent_static_ranges.txt), 740 static ranges run the keys-only sort at 2^28
+// in 5.99 ms instead of 3.76 ms.  The CTAs of a wave then write 740 x 256 run fronts that are
+// megabytes apart instead of 256 fronts a wave's tiles share: ncu shows 1.31x the algorithmic DRAM
+// traffic (partially written sectors are evicted before the same CTA's next tile extends them)
+// and every SM keeps > 1000 distinct 2 MB pages hot.  Short ranges handed out in order by the
+// hardware CTA scheduler keep the wave's working set as compact as one-tile CTAs do.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxRanges = 8192;  // rows of the range table
+constexpr int kMinRangeTiles = 8;
+
+// Tiles [first, first + count) of range r.
+__device__ __forceinline__ void RangeOf(uint32_t tiles, uint32_t range_tiles, uint32_t r, uint32_t& first, uint32_t& count) {
+  const uint64_t f = (uint64_t)r * range_tiles;
+  first = f < tiles ? (uint32_t)f : tiles;
+  count = tiles - first < range_tiles ? tiles - first : range_tiles;
+}
+
+template <class Cfg, bool GENERIC, int RANK = VRDX_RANK>
+__global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinCtas)
+RangePassKernel(const PassArgs a) {
+  constexpr int THREADS = Cfg::kThreads;
+  constexpr int IPT = Cfg::kItems;
+  constexpr bool KV = Cfg::kKeyValue;
+  constexpr int kWarps = Cfg::kWarps;
+  constexpr int kTile = Cfg::kTile;
+
+  extern __shared__ __align__(128) uint32_t smem[];
+  const TileSmem<Cfg> sm(smem);
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const uint32_t pass = a.pass;
+  const uint32_t n = ResolveCount(a.indirect, a.n_or_max);
+  GridDepLaunch();
+  {
+    uint4* z = reinterpret_cast<uint4*>(sm.cnt);
+#pragma unroll
+    for (int j = tid; j < kWarps * kRadix / 4; j += THREADS) z[j] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  GridDepWait();
+  const bool order_free = !KV && a.order_free != 0u;
+  const PassDigit<GENERIC> dg = MakePassDigit<Cfg, GENERIC>(a, order_free);
+  const uint32_t tiles = (uint32_t)CeilDiv((uint64_t)n, (uint64_t)kTile);
+  uint32_t tile, range_tiles;
+  RangeOf(tiles, a.range_tiles, blockIdx.x, tile, range_tiles);
+  if (range_tiles == 0) return;  // indirect count below max: surplus CTAs retire
+  const uint32_t tile_end = tile + range_tiles;
+
+  if (a.hdr->pass_identity[pass]) {
+    for (; tile < tile_end; ++tile) {
+      const uint64_t start = (uint64_t)tile * kTile;
+      const uint32_t rest = (uint32_t)(n - start);
+      TileCopy<Cfg, GENERIC>(a, start, rest < (uint32_t)kTile ? rest : (uint32_t)kTile, tid, dg);
+    }
+    StampEnd(a.ts_end);
+    return;
+  }
+
+  // digit thread: global slot of the next key of digit `tid` this range writes
+  uint32_t run = 0;
+  if (tid < kRadix) run = a.hdr->global_hist[pass][tid] + a.status[(size_t)blockIdx.x * kRadix + tid];
+
+  uint32_t key[IPT];
+  const uint32_t woff = warp * 32 * IPT + lane;
+  uint32_t* const row = sm.cnt + warp * kRadix;
+  {
+    const uint64_t start = (uint64_t)tile * kTile;
+    const uint32_t rest = (uint32_t)(n - start);
+    TileLoadKeys<Cfg, GENERIC>(key, a.keys_in, start, rest < (uint32_t)kTile ? rest : (uint32_t)kTile, woff, dg);
+  }
+  __syncthreads();  // counters zeroed
+
+  for (;;) {
+    const uint64_t tile_start = (uint64_t)tile * kTile;
+    const uint32_t remaining = (uint32_t)(n - tile_start);
+    const uint32_t tile_count = remaining < (uint32_t)kTile ? remaining : (uint32_t)kTile;
+
+    uint32_t rank2[IPT / 2];
+    TileRank<Cfg, GENERIC, RANK>(key, rank2, row, tile_count == (uint32_t)kTile, dg);
+    __syncthreads();
+
+    uint32_t digit_count = 0, digit_excl = 0;
+    uint32_t wcount[kWarps];
+    if (tid < kRadix) TileDigitSums<Cfg>(sm, wcount, digit_count, digit_excl, tile_count, dg.mask, tid);
+    __syncthreads();
+    if (tid < kRadix) {
+      TileSlotBases<Cfg>(sm, wcount, digit_excl, tid);
+      sm.gbase[tid] = run - (digit_excl >> 2);  // read only after the next barrier; last read two barriers ago
+      run += digit_count;
+    }
+    __syncthreads();
+
+    TileReorder<Cfg, GENERIC>(sm, key, rank2, row, a.vals_in, tile_start, tile_count, woff, dg);
+    // this warp's counter row is free again (only this warp reads its slot bases): zero it for the next tile
+    __syncwarp();
+    {
+      uint4* z = reinterpret_cast<uint4*>(row);
+      z[lane] = make_uint4(0u, 0u, 0u, 0u);
+      z[lane + 32] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    // next tile's keys: in flight while this tile is scattered
+    const bool more = tile + 1 < tile_end;
+#ifndef VRDX_RANGE_PREFETCH
+#define VRDX_RANGE_PREFETCH 1
+#endif
+    if (VRDX_RANGE_PREFETCH && more) {
+      const uint64_t next = tile_start + kTile;
+      const uint32_t rest = (uint32_t)(n - next);
+      TileLoadKeys<Cfg, GENERIC>(key, a.keys_in, next, rest < (uint32_t)kTile ? rest : (uint32_t)kTile, woff, dg);
+    }
+    __syncthreads();
+
+    TileScatter<Cfg, GENERIC>(sm, a.keys_out, a.vals_out, tile_count, tid, dg);
+    if (!more) break;
+    ++tile;
+    if (!VRDX_RANGE_PREFETCH) {
+      const uint64_t next = (uint64_t)tile * kTile;
+      const uint32_t rest = (uint32_t)(n - next);
+      TileLoadKeys<Cfg, GENERIC>(key, a.keys_in, next, rest < (uint32_t)kTile ? rest : (uint32_t)kTile, woff, dg);
+    }
+    // no barrier here: the next write to keys / vals / gbase comes after the next tile's three barriers,
+    // the counters of a warp are touched by that warp alone until the first of them
+  }
+  StampEnd(a.ts_end);
+}
+
+// UpsweepRangeKernel — the upsweep that goes with RangePassKernel: CTA r counts the digits of ALL tiles
+// of range r into one shared histogram and writes one row range_counts[r][256].  4 B/key read, no
+// per-tile output.  Launched with the same grid and range_tiles as RangePassKernel.
+template <int TILE>
+__global__ void __launch_bounds__(kUpsweepThreads)
+UpsweepRangeKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t range_tiles, uint32_t shift,
+                   uint32_t mask, const KeyCodec codec_in, const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ range_counts,
+                   StorageHeader* __restrict__ hdr, unsigned long long* ts_end) {
+  constexpr int THREADS = kUpsweepThreads;
+  static_assert(THREADS == kRadix, "one thread per digit");
+  __shared__ uint32_t h[kRadix];
+  const int tid = threadIdx.x;
+  GridDepLaunch();
+  const uint32_t n = ResolveCount(indirect, n_or_max);
+  const uint32_t tiles = (uint32_t)CeilDiv((uint64_t)n, (uint64_t)TILE);
+  uint32_t first, count;
+  RangeOf(tiles, range_tiles, blockIdx.x, first, count);
+  h[tid] = 0;
+  GridDepWait();
+  if (blockIdx.x == 0 && tid == 0) hdr->hist_blocks_done = 0;  // counter of this pass's SpineReduceKernel
+  __syncthreads();
+  constexpr int kIters = (TILE + THREADS - 1) / THREADS;
+  for (uint32_t tile = first; tile < first + count; ++tile) {
+    const uint64_t tile_start = (uint64_t)tile * TILE;
+    const uint32_t remaining = (uint32_t)(n - tile_start);
+    const uint32_t tile_count = remaining < (uint32_t)TILE ? remaining : (uint32_t)TILE;
+    const uint32_t* kin = keys_in + tile_start;
+    if (tile_count == (uint32_t)TILE) {
+      uint32_t k[kIters];
+#pragma unroll
+      for (int i = 0; i < kIters; ++i) k[i] = LdStream(kin + i * THREADS + tid);
+#pragma unroll
+      for (int i = 0; i < kIters; ++i) atomicAdd(&h[(KeyIn(k[i], codec_in) >> shift) & mask], 1u);
+    } else {
+#pragma unroll
+      for (int i = 0; i < kIters; ++i) {
+        const uint32_t idx = i * THREADS + tid;
+        if (idx < tile_count) atomicAdd(&h[(KeyIn(LdStream(kin + idx), codec_in) >> shift) & mask], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  range_counts[(size_t)blockIdx.x * kRadix + tid] = h[tid];  // ranges without tiles write zeros
+  StampEnd(ts_end);
+}
+
 
 }  // namespace vrdx

@@ -365,9 +365,12 @@ struct PassArgs {
   KeyCodec codec_in;    // non-zero only on the first pass: caller's key type/order -> sortable word
   KeyCodec codec_out;   // non-zero only on the last pass: sortable word -> caller's key type/order
   uint32_t order_free;  // 1: keys-only first pass of a sort over all 32 bits (no order to preserve)
+  uint32_t range_tiles; // RangePassKernel / UpsweepRangeKernel (VRDX_EXPERIMENTS): consecutive tiles per CTA
+  uint32_t words_only;  // 1: keys-only sort over all 32 bits (any pass): equal words are indistinguishable, so
+                        //    keys that agree in every bit below this pass's digit may swap places (PassKernel)
 };
 
-constexpr int kSpineChunk = 8;         // reduce-then-scan: tiles per upsweep CTA / spine chunk
+constexpr int kSpineChunk = (int)kSpineChunkTiles;  // reduce-then-scan: tiles per upsweep CTA / spine chunk
 constexpr int kRepairBallotThreshold = 12;  // colliding lanes above which the 8-round ballot loop is cheaper
 
 template <int THREADS, int IPT, bool KV, int MIN_CTAS, int LOOK_BATCH = 4, bool PAIRED = false>
@@ -395,6 +398,34 @@ struct PassConfig {
 #ifndef VRDX_LOOK_WIDE
 #define VRDX_LOOK_WIDE 4  // cells per round trip after the first (prefetched) batch; 12 and 24 measured slower
 #endif
+// One round trip of the walk: W cells in flight, consumed strictly nearest-first.
+// (A 32-cell "burst" round for sorts whose tiles are all co-resident — where a tile walks back over every
+// predecessor — was measured and changed nothing: small sorts are bound by the launch / drain latency of
+// their six dependent kernels, not by the walk; profiles/r02/e_small_n_shapes_burst_*.txt.)
+template <int W>
+__device__ __forceinline__ void LookBackRound(const uint32_t* status, int digit, uint32_t& look, uint32_t& excl, bool& done,
+                                              uint32_t& st_cells, uint32_t& st_notready) {
+  uint32_t w[W];
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    const uint32_t t = (look >= (uint32_t)j) ? look - j : 0u;
+    w[j] = LdRelaxed(status + (size_t)t * kRadix + digit);
+  }
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    if (done) break;
+    const uint32_t s = w[j];
+    if ((s >> 30) == 0u) {
+      ++st_notready;
+      break;
+    }
+    excl += s & kStatusValueMask;
+    ++st_cells;
+    if (s & kStatusPrefix) { done = true; break; }
+    --look;
+  }
+}
+
 template <int kLookBatch>
 __device__ __forceinline__ uint32_t LookBack(const uint32_t* status, uint32_t tile, int digit,
                                              uint32_t (&look_s)[kLookBatch], uint32_t* stats = nullptr) {
@@ -402,9 +433,7 @@ __device__ __forceinline__ uint32_t LookBack(const uint32_t* status, uint32_t ti
   uint32_t excl = 0;
   uint32_t look = tile - 1;  // nearest tile not yet consumed
   bool done = false;
-#ifdef VRDX_STATS
   uint32_t st_rounds = 1, st_cells = 0, st_notready = 0;
-#endif
   // first batch: the cells prefetched by the caller before the reorder
 #pragma unroll
   for (int j = 0; j < kLookBatch; ++j) {
@@ -412,41 +441,14 @@ __device__ __forceinline__ uint32_t LookBack(const uint32_t* status, uint32_t ti
     const uint32_t s = look_s[j];
     if ((s >> 30) == 0u) break;  // not published yet: re-poll from `look`
     excl += s & kStatusValueMask;
-#ifdef VRDX_STATS
     ++st_cells;
-#endif
     if (s & kStatusPrefix) { done = true; break; }
     --look;
   }
-  // later rounds: the walk is ~20 cells deep at full speed (profiles/r01_lookback_depth_stats.txt),
-  // so fetch a wider window per round trip; cells are still consumed strictly nearest-first
+  // later rounds: the walk is ~20 cells deep at full speed (profiles/r01_lookback_depth_stats.txt)
   while (!done) {
-#ifdef VRDX_STATS
     ++st_rounds;
-#endif
-    uint32_t w[kWide];
-#pragma unroll
-    for (int j = 0; j < kWide; ++j) {
-      const uint32_t t = (look >= (uint32_t)j) ? look - j : 0u;
-      w[j] = LdRelaxed(status + (size_t)t * kRadix + digit);
-    }
-#pragma unroll
-    for (int j = 0; j < kWide; ++j) {
-      if (done) break;
-      const uint32_t s = w[j];
-      if ((s >> 30) == 0u) {
-#ifdef VRDX_STATS
-        ++st_notready;
-#endif
-        break;
-      }
-      excl += s & kStatusValueMask;
-#ifdef VRDX_STATS
-      ++st_cells;
-#endif
-      if (s & kStatusPrefix) { done = true; break; }
-      --look;
-    }
+    LookBackRound<kWide>(status, digit, look, excl, done, st_cells, st_notready);
   }
 #ifdef VRDX_STATS
   if (stats != nullptr && digit == 0) {  // one sample per tile (digit 0)
@@ -455,6 +457,7 @@ __device__ __forceinline__ uint32_t LookBack(const uint32_t* status, uint32_t ti
     atomicAdd(stats + 2, st_notready);
   }
 #endif
+  (void)st_rounds;
   return excl;
 }
 
@@ -564,104 +567,76 @@ __device__ __forceinline__ uint32_t RepairRank(uint32_t d, uint32_t old, uint32_
   return r;
 }
 
-template <class Cfg, int MODE, bool GENERIC, int RANK = VRDX_RANK>
-__global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinCtas)
-PassKernel(const PassArgs a) {
-  constexpr int THREADS = Cfg::kThreads;
+// ---- the phases of one tile, shared by PassKernel (one tile per CTA) and RangePassKernel (a
+// ---- persistent CTA walking a contiguous range of tiles) ---------------------------------------
+
+// Shared-memory carve-up of a tile: cnt[kWarps][256] | keys[kTile] | vals[kTile] (KV) | gbase[256] | misc
+template <class Cfg>
+struct TileSmem {
+  uint32_t *cnt, *keys, *vals, *gbase, *misc;
+  __device__ __forceinline__ explicit TileSmem(uint32_t* base) {
+    cnt = base;                                              // warp-private digit counters (bytes), later slot bases
+    keys = cnt + Cfg::kWarps * kRadix;                       // tile reordered by digit
+    vals = keys + Cfg::kTile;                                // (KV only)
+    gbase = vals + (Cfg::kKeyValue ? Cfg::kTile : 0);        // global slot of tile-local slot 0, per digit
+    misc = gbase + kRadix;                                   // [0..7] warp totals, [8] tile id
+  }
+};
+
+// Digit plan and codecs of a pass as the tile phases use them.
+template <bool GENERIC>
+struct PassDigit {
+  uint32_t shift, mask, lowmask;  // shift: PRMT selector (reference plan) or bit shift (generic)
+  KeyCodec cin, cout;
+};
+
+// load: warp-striped, 128 B per warp-instruction.  Tail tile: pads are the largest word, rank after
+// every real key and are never stored (the reference pads the same way, downsweep.slang:81,85).
+template <class Cfg, bool GENERIC>
+__device__ __forceinline__ void TileLoadKeys(uint32_t (&key)[Cfg::kItems], const uint32_t* keys_in, uint64_t tile_start,
+                                             uint32_t tile_count, uint32_t woff, const PassDigit<GENERIC>& dg) {
+  constexpr int IPT = Cfg::kItems;
+  const uint32_t* kin = keys_in + tile_start + woff;
+  if (tile_count == (uint32_t)Cfg::kTile) {
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) key[i] = KeyIn(LdStream(kin + 32 * i), dg.cin);
+  } else {
+#pragma unroll
+    for (int i = 0; i < IPT; ++i)
+      key[i] = (woff + 32 * i < tile_count) ? KeyIn(LdStream(kin + 32 * i), dg.cin) : 0xFFFFFFFFu;
+  }
+}
+
+// warp-level multi-split: rank (bytes) of each key among equal digits inside its warp, two ranks per
+// register (they stay below 2^16 even after the slot base is added: kTile <= 2^14).
+template <class Cfg, bool GENERIC, int RANK>
+__device__ __forceinline__ void TileRank(const uint32_t (&key)[Cfg::kItems], uint32_t (&rank2)[Cfg::kItems / 2],
+                                         uint32_t* row, bool full, const PassDigit<GENERIC>& dg) {
   constexpr int IPT = Cfg::kItems;
   constexpr bool KV = Cfg::kKeyValue;
-  constexpr int kWarps = Cfg::kWarps;
-  constexpr int kTile = Cfg::kTile;
-  constexpr int kLookBatch = Cfg::kLookBatch;
-  static_assert(MODE == 0 || MODE == 1, "onesweep or reduce-then-scan");
-
-  extern __shared__ __align__(128) uint32_t smem[];
-  uint32_t* s_cnt = smem;                             // [kWarps][256] warp-private digit counters (bytes), later slot bases
-  uint32_t* s_keys = s_cnt + kWarps * kRadix;         // [kTile] tile reordered by digit
-  uint32_t* s_vals = s_keys + kTile;                  // [kTile] (KV only)
-  uint32_t* s_gbase = s_vals + (KV ? kTile : 0);      // [256] global slot of tile-local slot 0, per digit
-  uint32_t* s_misc = s_gbase + kRadix;                // [0..7] warp totals, [8] tile id
-
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int warp = tid >> 5;
-  const uint32_t pass = a.pass;
-  const uint32_t shift = GENERIC ? a.shift : (0x4440u | pass);  // reference plan: the PRMT selector of byte `pass`
-  const uint32_t mask = GENERIC ? a.mask : (uint32_t)(kRadix - 1);
-  const KeyCodec cin = GENERIC ? a.codec_in : KeyCodec{0u, 0u, 0u};
-  const KeyCodec cout = GENERIC ? a.codec_out : KeyCodec{0u, 0u, 0u};
-  const uint32_t n = ResolveCount(a.indirect, a.n_or_max);
-  GridDepLaunch();
-  {
-    uint4* z = reinterpret_cast<uint4*>(s_cnt);
+  // Which order must equal digits keep?  The input of pass p is sorted by the bits below digit p, and the
+  // output must be sorted by those bits within every digit.  Keys-only, all 32 bits compared: two keys
+  // that agree in all the lower bits may swap places without changing ANY later result (equal words are
+  // indistinguishable at the end).  So when all 32*IPT keys of this warp agree in the bits below the
+  // digit — always in pass 0, and in passes 1 and 2 of a large sort almost always, because a warp's
+  // 512 consecutive keys lie inside one run of the previous passes' order — any bijective ranking
+  // inside (warp, digit) will do, and the value returned by the atomic is one: no read-back, no
+  // repair.  Everything else (key-value sorts, bit sub-ranges, warps that straddle a run boundary,
+  // the tail tile whose pads must rank last) is ranked stably below.
+  bool relaxed = false;
+  if (!KV && full && dg.lowmask != 0xFFFFFFFFu) {
+    uint32_t diff = 0;
 #pragma unroll
-    for (int j = tid; j < kWarps * kRadix / 4; j += THREADS) z[j] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = 1; i < IPT; ++i) diff |= key[i] ^ key[0];
+    int same = 0;
+    __match_all_sync(0xffffffffu, key[0] & dg.lowmask, &same);
+    relaxed = __all_sync(0xffffffffu, (diff & dg.lowmask) == 0u) && same != 0;
   }
-  GridDepWait();  // everything below reads what the previous kernel of this sort wrote
-  // keys-only first pass of a sort over all 32 bits: no earlier order to preserve (see the ranking below)
-  const bool order_free = !KV && a.order_free != 0u;
-  const bool unordered = (MODE == 0) && order_free;
-  if (MODE == 0 && !unordered && tid == 0) s_misc[8] = atomicAdd(&a.hdr->tickets[pass], 1u);
-  __syncthreads();
-
-  const uint32_t tile = (MODE == 0 && !unordered) ? s_misc[8] : blockIdx.x;
-  const uint64_t tile_start = (uint64_t)tile * kTile;
-  if (tile_start >= n) return;  // indirect count below max: surplus CTAs retire (upsweep.slang:20-22)
-  const uint32_t remaining = (uint32_t)(n - tile_start);
-  const uint32_t tile_count = remaining < (uint32_t)kTile ? remaining : (uint32_t)kTile;
-  const bool full = tile_count == (uint32_t)kTile;
-
-  if (MODE == 0 && a.status_next != nullptr && tid < kRadix) a.status_next[(size_t)tile * kRadix + tid] = 0;
-
-  // ---- constant digit: a stable counting sort with one non-empty bucket is a copy --------------
-  if (a.hdr->pass_identity[pass]) {
-    const uint32_t* kin = a.keys_in + tile_start;
-    uint32_t* kout = a.keys_out + tile_start;
-    uint32_t ck[IPT], cv[KV ? IPT : 1];
-#pragma unroll
-    for (int i = 0; i < IPT; ++i) {  // all loads first: the stores below may alias them as far as the compiler knows
-      const uint32_t idx = i * THREADS + tid;
-      ck[i] = idx < tile_count ? KeyOut(KeyIn(LdStream(kin + idx), cin), cout) : 0u;
-      if (KV) cv[i] = idx < tile_count ? LdStream(a.vals_in + tile_start + idx) : 0u;
-    }
-#pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      const uint32_t idx = i * THREADS + tid;
-      if (idx < tile_count) {
-        kout[idx] = ck[i];
-        if (KV) a.vals_out[tile_start + idx] = cv[i];
-      }
-    }
-    StampEnd(a.ts_end);
-    return;
-  }
-
-  // ---- load: warp-striped, 128 B per warp-instruction -------------------------------------
-  uint32_t key[IPT];
-  const uint32_t woff = warp * 32 * IPT + lane;
-  {
-    const uint32_t* kin = a.keys_in + tile_start + woff;
-    if (full) {
-#pragma unroll
-      for (int i = 0; i < IPT; ++i) key[i] = KeyIn(LdStream(kin + 32 * i), cin);
-    } else {
-      // tail tile: pads are the largest word, rank after every real key and are never stored
-#pragma unroll
-      for (int i = 0; i < IPT; ++i)
-        key[i] = (woff + 32 * i < tile_count) ? KeyIn(LdStream(kin + 32 * i), cin) : 0xFFFFFFFFu;
-    }
-  }
-
-  // ---- warp-level multi-split: rank (bytes) of each key among equal digits inside its warp ----
-  // Ranks stay below 2^16 even after the slot base is added (kTile * 4 <= 2^16 is not required:
-  // kTile <= 2^14), so two of them share a register: 8 registers less than one per key.
-  uint32_t rank2[IPT / 2];
-  uint32_t* const row = s_cnt + warp * kRadix;
-  if (order_free && full) {
+  if (relaxed) {
 #pragma unroll
     for (int i = 0; i < IPT; i += 2) {
-      const uint32_t r0 = atomicAdd(row + DigitOf<GENERIC>(key[i], shift, mask), 4u);
-      const uint32_t r1 = atomicAdd(row + DigitOf<GENERIC>(key[i + 1], shift, mask), 4u);
+      const uint32_t r0 = atomicAdd(row + DigitOf<GENERIC>(key[i], dg.shift, dg.mask), 4u);
+      const uint32_t r1 = atomicAdd(row + DigitOf<GENERIC>(key[i + 1], dg.shift, dg.mask), 4u);
       rank2[i / 2] = __byte_perm(r0, r1, 0x5410);
     }
   } else {
@@ -670,7 +645,7 @@ PassKernel(const PassArgs a) {
     uint32_t d_prev = 0, old_prev = 0, fin_prev = 0, r_even = 0;
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
-      const uint32_t d = DigitOf<GENERIC>(key[i], shift, mask);
+      const uint32_t d = DigitOf<GENERIC>(key[i], dg.shift, dg.mask);
       volatile uint32_t* c = row + d;
       const uint32_t old = atomicAdd(row + d, 4u);  // optimistic: exact if no other lane holds digit d
       RankFence();
@@ -687,7 +662,7 @@ PassKernel(const PassArgs a) {
     uint32_t r_even = 0;
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
-      const uint32_t d = DigitOf<GENERIC>(key[i], shift, mask);
+      const uint32_t d = DigitOf<GENERIC>(key[i], dg.shift, dg.mask);
       volatile uint32_t* c = row + d;
       const uint32_t old = atomicAdd(row + d, 4u);  // optimistic: exact if no other lane holds digit d
       RankFence();
@@ -698,42 +673,222 @@ PassKernel(const PassArgs a) {
     }
 #endif
   }
+}
+
+// per-digit, first half (threads < 256, between two barriers): counts over warps -> this tile's count of
+// digit `tid` (pads removed) and its exclusive prefix inside the digit thread's warp (bytes).
+template <class Cfg>
+__device__ __forceinline__ void TileDigitSums(const TileSmem<Cfg>& sm, uint32_t (&wcount)[Cfg::kWarps], uint32_t& digit_count,
+                                              uint32_t& digit_excl, uint32_t tile_count, uint32_t mask, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  uint32_t sum = 0;
+#pragma unroll
+  for (int w = 0; w < Cfg::kWarps; ++w) {
+    wcount[w] = sm.cnt[w * kRadix + tid];
+    sum += wcount[w];
+  }
+  // pads were counted as the largest digit of this pass; they are not part of the data
+  digit_count = (sum >> 2) - (((uint32_t)tid == mask) ? ((uint32_t)Cfg::kTile - tile_count) : 0u);
+  const uint32_t incl = WarpInclusiveScan(sum, lane);
+  if (lane == 31) sm.misc[warp] = incl;
+  digit_excl = incl - sum;
+}
+// second half: tile-wide exclusive prefix of the digit (bytes); cnt becomes the tile-local byte offset of
+// the first key of every (warp, digit).
+template <class Cfg>
+__device__ __forceinline__ void TileSlotBases(const TileSmem<Cfg>& sm, const uint32_t (&wcount)[Cfg::kWarps],
+                                              uint32_t& digit_excl, int tid) {
+  const int warp = tid >> 5;
+#pragma unroll
+  for (int w = 0; w < kRadix / 32; ++w) digit_excl += (w < warp) ? sm.misc[w] : 0u;
+  uint32_t run = digit_excl;
+#pragma unroll
+  for (int w = 0; w < Cfg::kWarps; ++w) {
+    sm.cnt[w * kRadix + tid] = run;
+    run += wcount[w];
+  }
+}
+
+// tile-local reorder through shared memory; values are fetched only now, so they do not occupy
+// registers during the ranking
+template <class Cfg, bool GENERIC>
+__device__ __forceinline__ void TileReorder(const TileSmem<Cfg>& sm, const uint32_t (&key)[Cfg::kItems],
+                                            const uint32_t (&rank2)[Cfg::kItems / 2], const uint32_t* row,
+                                            const uint32_t* vals_in, uint64_t tile_start, uint32_t tile_count, uint32_t woff,
+                                            const PassDigit<GENERIC>& dg) {
+  constexpr int IPT = Cfg::kItems;
+  constexpr bool KV = Cfg::kKeyValue;
+  char* const keys_b = reinterpret_cast<char*>(sm.keys);
+  uint32_t slot_b[KV ? IPT : 1];  // byte offset of each key's slot (kept for the values only)
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    const uint32_t r = (i & 1) ? (rank2[i / 2] >> 16) : (rank2[i / 2] & 0xFFFFu);
+    const uint32_t sb = r + row[DigitOf<GENERIC>(key[i], dg.shift, dg.mask)];
+    *reinterpret_cast<uint32_t*>(keys_b + sb) = key[i];
+    if (KV) slot_b[i] = sb;
+  }
+  if (KV) {
+    const uint32_t* vin = vals_in + tile_start + woff;
+    uint32_t val[IPT];
+    if (tile_count == (uint32_t)Cfg::kTile) {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) val[i] = LdStream(vin + 32 * i);
+    } else {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) val[i] = (woff + 32 * i < tile_count) ? LdStream(vin + 32 * i) : 0u;
+    }
+    char* const vals_b = reinterpret_cast<char*>(sm.vals);
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) *reinterpret_cast<uint32_t*>(vals_b + slot_b[i]) = val[i];
+  }
+}
+
+// scatter: consecutive threads write consecutive slots of a digit run
+template <class Cfg, bool GENERIC>
+__device__ __forceinline__ void TileScatter(const TileSmem<Cfg>& sm, uint32_t* keys_out, uint32_t* vals_out,
+                                            uint32_t tile_count, int tid, const PassDigit<GENERIC>& dg) {
+  constexpr int IPT = Cfg::kItems;
+  constexpr int THREADS = Cfg::kThreads;
+  constexpr bool KV = Cfg::kKeyValue;
+  if (tile_count == (uint32_t)Cfg::kTile) {
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const uint32_t slot = i * THREADS + tid;
+      const uint32_t k = sm.keys[slot];
+      const uint32_t g = sm.gbase[DigitOf<GENERIC>(k, dg.shift, dg.mask)] + slot;
+      keys_out[g] = KeyOut(k, dg.cout);
+      if (KV) vals_out[g] = sm.vals[slot];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const uint32_t slot = i * THREADS + tid;
+      if (slot < tile_count) {
+        const uint32_t k = sm.keys[slot];
+        const uint32_t g = sm.gbase[DigitOf<GENERIC>(k, dg.shift, dg.mask)] + slot;
+        keys_out[g] = KeyOut(k, dg.cout);
+        if (KV) vals_out[g] = sm.vals[slot];
+      }
+    }
+  }
+}
+
+// constant digit: a stable counting sort with one non-empty bucket is a copy of [start, start + count)
+template <class Cfg, bool GENERIC>
+__device__ __forceinline__ void TileCopy(const PassArgs& a, uint64_t tile_start, uint32_t tile_count, int tid,
+                                         const PassDigit<GENERIC>& dg) {
+  constexpr int IPT = Cfg::kItems;
+  constexpr int THREADS = Cfg::kThreads;
+  constexpr bool KV = Cfg::kKeyValue;
+  const uint32_t* kin = a.keys_in + tile_start;
+  uint32_t* kout = a.keys_out + tile_start;
+  uint32_t ck[IPT], cv[KV ? IPT : 1];
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {  // all loads first: the stores below may alias them as far as the compiler knows
+    const uint32_t idx = i * THREADS + tid;
+    ck[i] = idx < tile_count ? KeyOut(KeyIn(LdStream(kin + idx), dg.cin), dg.cout) : 0u;
+    if (KV) cv[i] = idx < tile_count ? LdStream(a.vals_in + tile_start + idx) : 0u;
+  }
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    const uint32_t idx = i * THREADS + tid;
+    if (idx < tile_count) {
+      kout[idx] = ck[i];
+      if (KV) a.vals_out[tile_start + idx] = cv[i];
+    }
+  }
+}
+
+template <class Cfg, bool GENERIC>
+__device__ __forceinline__ PassDigit<GENERIC> MakePassDigit(const PassArgs& a, bool order_free) {
+  PassDigit<GENERIC> dg;
+  dg.shift = GENERIC ? a.shift : (0x4440u | a.pass);  // reference plan: the PRMT selector of byte `pass`
+  dg.mask = GENERIC ? a.mask : (uint32_t)(kRadix - 1);
+  dg.cin = GENERIC ? a.codec_in : KeyCodec{0u, 0u, 0u};
+  dg.cout = GENERIC ? a.codec_out : KeyCodec{0u, 0u, 0u};
+  // bits below this pass's digit (a keys-only sort over all 32 bits has contiguous digits from bit 0)
+  dg.lowmask = (!Cfg::kKeyValue && a.words_only != 0u) ? ((1u << (GENERIC ? a.shift : a.pass * kRadixBits)) - 1u)
+               : order_free                            ? 0u
+                                                       : 0xFFFFFFFFu;
+  return dg;
+}
+
+template <class Cfg, int MODE, bool GENERIC, int RANK = VRDX_RANK>
+__global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinCtas)
+PassKernel(const PassArgs a) {
+  constexpr int THREADS = Cfg::kThreads;
+  constexpr int IPT = Cfg::kItems;
+  constexpr bool KV = Cfg::kKeyValue;
+  constexpr int kWarps = Cfg::kWarps;
+  constexpr int kTile = Cfg::kTile;
+  constexpr int kLookBatch = Cfg::kLookBatch;
+  static_assert(MODE == 0 || MODE == 1, "onesweep or reduce-then-scan (per-tile tables)");
+
+  extern __shared__ __align__(128) uint32_t smem[];
+  const TileSmem<Cfg> sm(smem);
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const uint32_t pass = a.pass;
+  const uint32_t n = ResolveCount(a.indirect, a.n_or_max);
+  GridDepLaunch();
+  {
+    uint4* z = reinterpret_cast<uint4*>(sm.cnt);
+#pragma unroll
+    for (int j = tid; j < kWarps * kRadix / 4; j += THREADS) z[j] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  GridDepWait();  // everything below reads what the previous kernel of this sort wrote
+  // keys-only first pass of a sort over all 32 bits: no earlier order to preserve (see TileRank), so an
+  // onesweep tile may also claim its output ranges with global atomics instead of tickets + look-back
+  const bool order_free = !KV && a.order_free != 0u;
+  const bool unordered = (MODE == 0) && order_free;
+  const PassDigit<GENERIC> dg = MakePassDigit<Cfg, GENERIC>(a, order_free);
+  // Tile ids are handed out in arrival order so that every predecessor a tile may wait on in the
+  // look-back is already resident (forward progress without relying on blockIdx order).
+  if (MODE == 0 && !unordered && tid == 0) sm.misc[8] = atomicAdd(&a.hdr->tickets[pass], 1u);
   __syncthreads();
 
-  // ---- per-digit: counts over warps, publish aggregate, tile-local exclusive scan (bytes) -----
+  const uint32_t tile = (MODE == 0 && !unordered) ? sm.misc[8] : blockIdx.x;
+  const uint64_t tile_start = (uint64_t)tile * kTile;
+  if (tile_start >= n) return;  // indirect count below max: surplus CTAs retire (upsweep.slang:20-22)
+  const uint32_t remaining = (uint32_t)(n - tile_start);
+  const uint32_t tile_count = remaining < (uint32_t)kTile ? remaining : (uint32_t)kTile;
+  const bool full = tile_count == (uint32_t)kTile;
+
+  if (MODE == 0 && a.status_next != nullptr && tid < kRadix) a.status_next[(size_t)tile * kRadix + tid] = 0;
+
+  if (a.hdr->pass_identity[pass]) {
+    TileCopy<Cfg, GENERIC>(a, tile_start, tile_count, tid, dg);
+    StampEnd(a.ts_end);
+    return;
+  }
+
+  uint32_t key[IPT];
+  const uint32_t woff = warp * 32 * IPT + lane;
+  TileLoadKeys<Cfg, GENERIC>(key, a.keys_in, tile_start, tile_count, woff, dg);
+
+  uint32_t rank2[IPT / 2];
+  uint32_t* const row = sm.cnt + warp * kRadix;
+  TileRank<Cfg, GENERIC, RANK>(key, rank2, row, full, dg);
+  __syncthreads();
+
   uint32_t digit_count = 0, digit_excl = 0;
   uint32_t wcount[kWarps];
   if (tid < kRadix) {
-    uint32_t sum = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-      wcount[w] = s_cnt[w * kRadix + tid];
-      sum += wcount[w];
-    }
-    // pads were counted as the largest digit of this pass; they are not part of the data
-    digit_count = (sum >> 2) - (((uint32_t)tid == mask) ? ((uint32_t)kTile - tile_count) : 0u);
+    TileDigitSums<Cfg>(sm, wcount, digit_count, digit_excl, tile_count, dg.mask, tid);
     if (MODE == 0 && !unordered)
       StRelaxed(a.status + (size_t)tile * kRadix + tid,
                 (tile == 0 ? kStatusPrefix : kStatusAggregate) | digit_count);
-    const uint32_t incl = WarpInclusiveScan(sum, lane);
-    if (lane == 31) s_misc[warp] = incl;
-    digit_excl = incl - sum;  // exclusive within the warp
   }
   __syncthreads();
   uint32_t look_s[kLookBatch];
   if (tid < kRadix) {
-#pragma unroll
-    for (int w = 0; w < kRadix / 32; ++w) digit_excl += (w < warp) ? s_misc[w] : 0u;
-    // s_cnt becomes the tile-local byte offset of the first key of (warp, digit)
-    uint32_t run = digit_excl;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-      s_cnt[w * kRadix + tid] = run;
-      run += wcount[w];
-    }
+    TileSlotBases<Cfg>(sm, wcount, digit_excl, tid);
     if (unordered) {
+      // claim [excl, excl + digit_count) of this digit's global run; the round trip overlaps the reorder
       look_s[0] = digit_count ? atomicAdd(&a.hdr->claim_cursor[tid], digit_count) : 0u;
     } else if (MODE == 0) {
+      // start the first batch of look-back loads now; it is consumed after the reorder below
 #pragma unroll
       for (int j = 0; j < kLookBatch; ++j) {
         const uint32_t t = (tile > (uint32_t)j) ? tile - 1 - j : 0u;
@@ -741,38 +896,13 @@ PassKernel(const PassArgs a) {
       }
     } else {
       // reduce-then-scan: scanned chunk prefix + this tile's exclusive prefix inside its chunk
-      look_s[0] = a.status_next[(size_t)(tile / kSpineChunk) * kRadix + tid] + a.status[(size_t)tile * kRadix + tid];
+      look_s[0] = a.status_next[(size_t)(tile / kSpineChunk) * kRadix + tid] +
+                  reinterpret_cast<const uint16_t*>(a.status)[(size_t)tile * kRadix + tid];
     }
   }
   __syncthreads();
 
-  // ---- tile-local reorder through shared memory --------------------------------------------
-  {
-    char* const keys_b = reinterpret_cast<char*>(s_keys);
-    uint32_t slot_b[KV ? IPT : 1];  // byte offset of each key's slot (kept for the values only)
-#pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      const uint32_t r = (i & 1) ? (rank2[i / 2] >> 16) : (rank2[i / 2] & 0xFFFFu);
-      const uint32_t sb = r + row[DigitOf<GENERIC>(key[i], shift, mask)];
-      *reinterpret_cast<uint32_t*>(keys_b + sb) = key[i];
-      if (KV) slot_b[i] = sb;
-    }
-    if (KV) {
-      // values are fetched only now, so they do not occupy registers during the ranking
-      const uint32_t* vin = a.vals_in + tile_start + woff;
-      uint32_t val[IPT];
-      if (full) {
-#pragma unroll
-        for (int i = 0; i < IPT; ++i) val[i] = LdStream(vin + 32 * i);
-      } else {
-#pragma unroll
-        for (int i = 0; i < IPT; ++i) val[i] = (woff + 32 * i < tile_count) ? LdStream(vin + 32 * i) : 0u;
-      }
-      char* const vals_b = reinterpret_cast<char*>(s_vals);
-#pragma unroll
-      for (int i = 0; i < IPT; ++i) *reinterpret_cast<uint32_t*>(vals_b + slot_b[i]) = val[i];
-    }
-  }
+  TileReorder<Cfg, GENERIC>(sm, key, rank2, row, a.vals_in, tile_start, tile_count, woff, dg);
 
   // ---- global offsets of the digit runs ----------------------------------------------------
   if (tid < kRadix) {
@@ -784,32 +914,11 @@ PassKernel(const PassArgs a) {
       StRelaxed(a.status + (size_t)tile * kRadix + tid, kStatusPrefix | (excl + digit_count));
     }
     // global slot of tile-local slot 0 for this digit (mod 2^32 arithmetic)
-    s_gbase[tid] = a.hdr->global_hist[pass][tid] + excl - (digit_excl >> 2);
+    sm.gbase[tid] = a.hdr->global_hist[pass][tid] + excl - (digit_excl >> 2);
   }
   __syncthreads();
 
-  // ---- scatter: consecutive threads write consecutive slots of a digit run -------------------
-  if (full) {
-#pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      const uint32_t slot = i * THREADS + tid;
-      const uint32_t k = s_keys[slot];
-      const uint32_t g = s_gbase[DigitOf<GENERIC>(k, shift, mask)] + slot;
-      a.keys_out[g] = KeyOut(k, cout);
-      if (KV) a.vals_out[g] = s_vals[slot];
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      const uint32_t slot = i * THREADS + tid;
-      if (slot < tile_count) {
-        const uint32_t k = s_keys[slot];
-        const uint32_t g = s_gbase[DigitOf<GENERIC>(k, shift, mask)] + slot;
-        a.keys_out[g] = KeyOut(k, cout);
-        if (KV) a.vals_out[g] = s_vals[slot];
-      }
-    }
-  }
+  TileScatter<Cfg, GENERIC>(sm, a.keys_out, a.vals_out, tile_count, tid, dg);
   StampEnd(a.ts_end);
 }
 
@@ -830,8 +939,10 @@ PassKernel(const PassArgs a) {
 // ------------------------------------------------------------------------------------------
 constexpr int kUpsweepThreads = 256;
 
-// EXCL: tile_hist[tile][d] holds the number of digit-d keys in the EARLIER tiles of the same chunk (what
-// PassKernel<.., 1> adds to the chunk prefix) instead of the tile's own count (OnesweepKernel<.., 1>).
+// EXCL: tile_hist is a table of 16-bit words, tile_hist[tile][d] = number of digit-d keys in the EARLIER
+// tiles of the same chunk (< kSpineChunk * TILE <= 2^16; what PassKernel<.., 1> adds to the chunk prefix):
+// half the bytes of the reference's partHist (h.in:353-362).  !EXCL (round-1 kernels, VRDX_EXPERIMENTS):
+// 32-bit words holding the tile's own count.
 template <int TILE, bool EXCL = false>
 __global__ void __launch_bounds__(kUpsweepThreads)
 UpsweepKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t shift, uint32_t mask,
@@ -839,6 +950,7 @@ UpsweepKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t
               uint32_t* __restrict__ chunk_sums, StorageHeader* __restrict__ hdr, unsigned long long* ts_end) {
   constexpr int THREADS = kUpsweepThreads;
   static_assert(THREADS == kRadix, "one thread per digit");
+  static_assert(!EXCL || (uint64_t)(kSpineChunk - 1) * TILE < 65536, "in-chunk prefixes are stored as 16-bit words");
   __shared__ uint32_t h[2][kRadix];
   const int tid = threadIdx.x;
   GridDepLaunch();
@@ -876,7 +988,8 @@ UpsweepKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t
     __syncthreads();  // one barrier per tile: the two histograms alternate
     const uint32_t c = hh[tid];
     hh[tid] = 0;      // ready for tile + 2 (the next tile uses the other buffer; barrier above orders it)
-    tile_hist[(size_t)tile * kRadix + tid] = EXCL ? chunk_acc : c;
+    if (EXCL) reinterpret_cast<uint16_t*>(tile_hist)[(size_t)tile * kRadix + tid] = (uint16_t)chunk_acc;
+    else tile_hist[(size_t)tile * kRadix + tid] = c;
     chunk_acc += c;
   }
   chunk_sums[(size_t)blockIdx.x * kRadix + tid] = chunk_acc;
@@ -890,26 +1003,29 @@ UpsweepKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t
 //                      scans seg over segments in place and turns the per-digit totals into the
 //                      global digit offsets hdr->global_hist[pass]
 //   SpineApplyKernel   CTA s rewrites the rows of segment s as exclusive prefixes
-constexpr int kSpineSegments = 128;
+constexpr int kSpineSegments = (int)kSpineSegmentRows;
 
 // The grid (number of segments) is sized by the host from maxElementCount; the rows are split
 // evenly over however many segments were launched, using the device-resident count.
-__device__ __forceinline__ void SpineGeometry(uint32_t n, uint32_t tile_size, uint32_t& chunks, uint32_t& rows_per) {
+// `fixed_rows` != 0: the table has exactly that many rows (one per persistent CTA, RangePassKernel).
+__device__ __forceinline__ void SpineGeometry(uint32_t n, uint32_t tile_size, uint32_t fixed_rows, uint32_t& chunks,
+                                              uint32_t& rows_per) {
   const uint32_t tiles = (uint32_t)CeilDiv(n, tile_size);
-  chunks = (uint32_t)CeilDiv(tiles, kSpineChunk);
+  chunks = fixed_rows ? fixed_rows : (uint32_t)CeilDiv(tiles, kSpineChunk);
   rows_per = (chunks + gridDim.x - 1) / gridDim.x;
 }
 
 __global__ void __launch_bounds__(kRadix)
-SpineReduceKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t tile_size, uint32_t pass,
-                  const uint32_t* __restrict__ chunk_sums, uint32_t* __restrict__ seg, StorageHeader* __restrict__ hdr) {
+SpineReduceKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t tile_size, uint32_t fixed_rows,
+                  uint32_t pass, const uint32_t* __restrict__ chunk_sums, uint32_t* __restrict__ seg,
+                  StorageHeader* __restrict__ hdr) {
   __shared__ uint32_t s_last;
   __shared__ uint32_t s_warp[kRadix / 32];
   GridDepLaunch();
   GridDepWait();
   const uint32_t n = ResolveCount(indirect, n_or_max);
   uint32_t chunks, rows_per;
-  SpineGeometry(n, tile_size, chunks, rows_per);
+  SpineGeometry(n, tile_size, fixed_rows, chunks, rows_per);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t r0 = blockIdx.x * rows_per;
   const uint32_t r1 = r0 + rows_per < chunks ? r0 + rows_per : chunks;
@@ -949,13 +1065,13 @@ SpineReduceKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint
 }
 
 __global__ void __launch_bounds__(kRadix)
-SpineApplyKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t tile_size,
+SpineApplyKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t tile_size, uint32_t fixed_rows,
                  uint32_t* __restrict__ chunk_sums, const uint32_t* __restrict__ seg, unsigned long long* ts_end) {
   GridDepLaunch();
   GridDepWait();
   const uint32_t n = ResolveCount(indirect, n_or_max);
   uint32_t chunks, rows_per;
-  SpineGeometry(n, tile_size, chunks, rows_per);
+  SpineGeometry(n, tile_size, fixed_rows, chunks, rows_per);
   const int tid = threadIdx.x;
   const uint32_t r0 = blockIdx.x * rows_per;
   const uint32_t r1 = r0 + rows_per < chunks ? r0 + rows_per : chunks;

@@ -2,10 +2,11 @@
 //
 // Replaces the reference's storage layout (src/vk_radix_sort.h.in:353-362):
 //   reference: [count 16 B][globalHist 4x256][partHist P x 256, P = ceil(N/4096)][keysAlt][valuesAlt]
-//   here:      [StorageHeader][status A: T x 256][status B: T x 256][keysAlt][valuesAlt]
-// where T = ceil(N / tile) tiles of the pass kernel and a status word is the decoupled
-// look-back cell (2 flag bits + 30-bit count).  In reduce-then-scan mode status A holds the
-// per-tile digit histograms (full 32-bit counts) and status B the per-chunk spine sums.
+//   here:      [StorageHeader][table A: R x 256][table B: R x 256][keysAlt][valuesAlt]
+// Onesweep (small and medium N): both tables hold one row of 256 decoupled look-back cells per tile (2 flag
+// bits + 30-bit count), alternating between passes.  Reduce-then-scan (large N): table A holds one row of
+// 256 SIXTEEN-bit in-chunk prefixes per tile (half of the reference's partHist), table B one 32-bit row per
+// chunk of 8 tiles + the spine's segment sums.  2^28 keys: 1,120 MB in total (reference: 1,141 MB).
 // All offsets are multiples of 16 bytes and all size arithmetic is 64-bit.
 #pragma once
 #include <stdint.h>
@@ -47,7 +48,7 @@ struct StorageLayout {
   uint64_t header_offset;
   uint64_t status_a_offset;
   uint64_t status_b_offset;
-  uint64_t status_bytes;  // per buffer
+  uint64_t status_a_bytes, status_b_bytes;
   uint64_t keys_alt_offset;
   uint64_t values_alt_offset;
   uint64_t inout_bytes;   // Align(4N, 16)
@@ -55,17 +56,33 @@ struct StorageLayout {
   uint64_t total_kv;      // size for key-value
 };
 
-// `min_tile` = smallest tile (keys per CTA) any kernel of this sorter may use for this count,
-// so the status buffers are large enough whichever kernel configuration runs.
-inline StorageLayout ComputeLayout(uint64_t max_count, uint32_t min_tile) {
+constexpr uint32_t kSpineChunkTiles = 8;     // reduce-then-scan: tiles per upsweep CTA / spine row
+constexpr uint32_t kSpineSegmentRows = 128;  // spine: segment sums kept after the chunk rows
+
+// `min_tile` = smallest tile (keys per CTA) any kernel of this sorter may use, so the tables are large
+// enough whichever kernel configuration runs.
+// `onesweep_below` = counts below this may be sorted by onesweep (AUTO: the measured crossover; ~0: every
+// count; 0: none).  Onesweep keeps two tables of 32-bit look-back cells, one row (256 cells) per tile.
+// Reduce-then-scan keeps table A = one row of 16-BIT in-chunk prefixes per tile and table B = one 32-bit row
+// per chunk of 8 tiles + the spine's segment sums.  `wide_rows`: the round-1 kernels (VRDX_EXPERIMENTS) keep
+// 32-bit rows in both.  Every term is non-decreasing in max_count: storage sized for maxElementCount also
+// serves any smaller count (the reference's formula is monotone too, h.in:279-308).
+inline StorageLayout ComputeLayout(uint64_t max_count, uint32_t min_tile, uint64_t onesweep_below = ~0ull,
+                                   bool wide_rows = false) {
   StorageLayout l{};
+  const uint64_t row = kRadix * sizeof(uint32_t);
   const uint64_t tiles = CeilDiv(max_count, min_tile) + 1;
+  const uint64_t one_count = onesweep_below == 0 ? 0 : (max_count < onesweep_below ? max_count : onesweep_below - 1);
+  const uint64_t one_bytes = one_count ? (CeilDiv(one_count, min_tile) + 1) * row : 0;
+  const uint64_t rts_a = wide_rows ? tiles * row : tiles * (row / 2);
+  const uint64_t rts_b = wide_rows ? tiles * row : (CeilDiv(tiles, kSpineChunkTiles) + kSpineSegmentRows + 1) * row;
   l.header_offset = 0;
   l.status_a_offset = AlignUp(sizeof(StorageHeader), kOffsetAlignment);
-  l.status_bytes = AlignUp(tiles * kRadix * sizeof(uint32_t), kOffsetAlignment);
-  l.status_b_offset = l.status_a_offset + l.status_bytes;
+  l.status_a_bytes = AlignUp(one_bytes > rts_a ? one_bytes : rts_a, kOffsetAlignment);
+  l.status_b_bytes = AlignUp(one_bytes > rts_b ? one_bytes : rts_b, kOffsetAlignment);
+  l.status_b_offset = l.status_a_offset + l.status_a_bytes;
   l.inout_bytes = AlignUp(max_count * sizeof(uint32_t), kOffsetAlignment);
-  l.keys_alt_offset = l.status_b_offset + l.status_bytes;
+  l.keys_alt_offset = l.status_b_offset + l.status_b_bytes;
   l.values_alt_offset = l.keys_alt_offset + l.inout_bytes;
   l.total_keys = l.values_alt_offset;
   l.total_kv = l.values_alt_offset + l.inout_bytes;
