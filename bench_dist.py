@@ -59,6 +59,22 @@ def verify_distributed(cpu_oracle, recv, recv_count, host_keys, n, world):
     return bool(ok.item()), [e[2] for e in edges]
 
 
+def nvlink_counters_kib(gpu_index: int):
+    """Sum of the NVLink data counters of one GPU (`nvidia-smi nvlink -gt d`): (tx KiB, rx KiB) or None."""
+    import re
+    import subprocess
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(gpu_index)], capture_output=True, text=True,
+                             timeout=20).stdout
+    except Exception:
+        return None
+    tx = [int(x) for x in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out)]
+    rx = [int(x) for x in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out)]
+    if not tx:
+        return None
+    return sum(tx), sum(rx)
+
+
 ADVERSARIAL = ("all_zero", "skewed", "bits4", "all_ones")   # BASELINE.json configs[3] distributions, across real GPUs
 
 
@@ -82,7 +98,7 @@ def run(args, metric, unit):
     pristine = torch.from_numpy(host_keys.view(np.int32)).cuda()
     keys = torch.empty_like(pristine)
     backend = CudaBackend(local_rank)
-    strategy = os.environ.get("VRDX_DIST_SPLITTERS", "exact")        # exact: N/G +- 1 keys per rank; sampled: ~1 % imbalance
+    strategy = os.environ.get("VRDX_DIST_SPLITTERS", "sampled")       # exact: N/G +- 1 keys per rank; sampled: ~1 % imbalance
     cap = n + (n >> 4) + 1024
     fused = os.environ.get("VRDX_DIST_EXCHANGE", "fused") != "nccl"
     shared = SharedReceive(backend, cap) if fused else None
@@ -133,6 +149,24 @@ def run(args, metric, unit):
 
     # ---- verification (untimed): local order, rank boundaries, global multiset ----------------------
     verified, _ = verify_distributed(cpu_oracle, recv, recv_count, host_keys, n, world)
+
+    # ---- NVLink evidence: the link counters of this rank's GPU around ONE more (untimed) step ----------
+    nvlink = None
+    if rank == 0:
+        before = nvlink_counters_kib(local_rank)
+    keys.copy_(pristine)
+    torch.cuda.synchronize()
+    dist.barrier()
+    distributed_sort(backend, keys, n, recv=recv, part=part, storage=storage, shared=shared, strategy=strategy)
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        after = nvlink_counters_kib(local_rank)
+        if before and after:
+            sent = sum(plan.sizes[rank][j] for j in range(world) if j != rank) * 4
+            nvlink = {"gpu": local_rank, "tx_bytes": (after[0] - before[0]) * 1024, "rx_bytes": (after[1] - before[1]) * 1024,
+                      "expected_key_bytes_out": sent,
+                      "source": "nvidia-smi nvlink -gt d, delta over one untimed distributed sort (keys + NCCL control traffic)"}
 
     # ---- adversarial parity across the real GPUs (untimed; the NCCL pytest is skipped on 1-GPU boxes, so
     #      the driver-observed exit code of this bench is what covers these) -----------------------------
@@ -200,6 +234,7 @@ def run(args, metric, unit):
                                      ((stages["exchange"] + (stages["partition"] if fused else 0.0)) * 1e-3) / 1e9)
             if world > 1 else None,
             "exchange": "fused peer stores (CUDA IPC over NVLink)" if fused else "NCCL all-to-all-v",
+            "nvlink_counters": nvlink,
             "e2e": {"value": world * n / (e2e_ms * 1e-3) / 1e9, "unit": unit, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 4 * n * world, "d2h_bytes_per_step": 4 * n * world,
                     "path": "per rank: pinned host keys -> H2D -> distributed sort (C-ABI kernels + NCCL) -> D2H of the sorted slice"},

@@ -551,7 +551,9 @@ VkResult vrdxCudaCreateSorter(const VrdxSorterCreateInfo* pCreateInfo,
       cudaFuncSetAttribute(HistogramKernelPrivate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)kHistPrivSmemBytes) != cudaSuccess ||
       cudaFuncSetAttribute(DistPrefixHistogramKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)kDistHistMaxSmemBytes) != cudaSuccess) {
+                           (int)kDistHistMaxSmemBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(DistClassCountKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)kDistCountSmemBytes) != cudaSuccess) {
     cudaGetLastError();
     return VK_ERROR_INITIALIZATION_FAILED;
   }
@@ -997,9 +999,9 @@ void vrdxDistCmdClassCount(VkCommandBuffer commandBuffer, VrdxSorter sorter, uin
       splittersBuffer ? reinterpret_cast<const uint32_t*>(reinterpret_cast<char*>(splittersBuffer) + splittersOffset)
                       : keys;
   uint32_t* counts = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(countsBuffer) + countsOffset);
-  const uint64_t blocks = CeilDiv((uint64_t)elementCount, (uint64_t)kDistHistThreads);
-  const uint64_t cap = (uint64_t)sorter->sm_count * 4;
-  DistClassCountKernel<<<(uint32_t)(blocks < cap ? blocks : cap), kDistHistThreads, 0, stream>>>(
+  const uint64_t blocks = CeilDiv((uint64_t)elementCount / 4 + 1, (uint64_t)kDistCountThreads * 4);
+  const uint64_t cap = (uint64_t)sorter->sm_count * 3;  // 64 KB of lane-private counters per CTA
+  DistClassCountKernel<<<(uint32_t)(blocks < cap ? (blocks ? blocks : 1) : cap), kDistCountThreads, kDistCountSmemBytes, stream>>>(
       keys, elementCount, splitterCount, splitters, counts);
   NoteError(sorter, cudaGetLastError());
 }

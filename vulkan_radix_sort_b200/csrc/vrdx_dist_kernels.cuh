@@ -11,6 +11,7 @@ namespace vrdx {
 
 constexpr int kDistMaxSplitters = 15;
 constexpr int kDistMaxClasses = 2 * kDistMaxSplitters + 1;
+constexpr int kDistClassSlotsForCount = 32;  // classes padded to a power of two (DistClassCountKernel)
 
 struct DistPrefixes {
   uint32_t count;
@@ -145,52 +146,70 @@ __device__ __noinline__ uint32_t DistClassOfSlow(uint32_t k, const uint32_t* s_u
 }
 
 // ---- class sizes (count only) ----------------------------------------------------------------------
-// Same class function as the multi-split below; warp-aggregated shared-memory counting (a class is
-// shared by many lanes, so peers are found with a ballot per class bit instead of colliding atomics).
-__global__ void __launch_bounds__(kDistHistThreads)
+// Same class function as the multi-split below.  4 B/key read with 128-bit loads; every (class, lane)
+// pair has its own shared-memory counter (address = class * 32 + lane, i.e. bank = lane), so the 32
+// atomics of a warp-instruction never collide however few classes there are (with 3 classes a plain
+// per-class counter would serialise ~11 lanes per instruction).  32 classes x 32 lanes x 16 warps = 64 KB.
+constexpr int kDistCountThreads = 512;
+constexpr size_t kDistCountSmemBytes = (size_t)(kDistCountThreads / 32) * kDistClassSlotsForCount * 32 * sizeof(uint32_t);
+
+__global__ void __launch_bounds__(kDistCountThreads)
 DistClassCountKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t splitter_count,
                      const uint32_t* __restrict__ splitters, uint32_t* __restrict__ counts) {
+  extern __shared__ __align__(16) uint32_t s_lane_cnt[];  // [warp][class][lane]
   __shared__ uint32_t s_u[kDistMaxSplitters];
   __shared__ __align__(16) uint8_t s_top[kDistLutSize];
-  __shared__ uint32_t s_cnt[32];
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < (int)splitter_count) s_u[tid] = splitters[tid];
-  if (tid < 32) s_cnt[tid] = 0;
-  DistBuildClassLut(s_top, splitters, splitter_count, tid, kDistHistThreads);
+  {
+    uint4* z = reinterpret_cast<uint4*>(s_lane_cnt);
+    for (int i = tid; i < (int)(kDistCountSmemBytes / 16); i += kDistCountThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  DistBuildClassLut(s_top, splitters, splitter_count, tid, kDistCountThreads);
   __syncthreads();
-  auto class_of = [&](uint32_t k) -> uint32_t {
-    const uint32_t t = s_top[k >> (32 - kDistLutBits)];
-    if (!(t & 0x80u)) return t;
-    return DistClassOfSlow(k, s_u, splitter_count);
+  uint32_t* mine = s_lane_cnt + warp * (kDistClassSlotsForCount * 32) + lane;
+  auto count_key = [&](uint32_t k) {
+    uint32_t c = s_top[k >> (32 - kDistLutBits)];
+    if (c & 0x80u) c = DistClassOfSlow(k, s_u, splitter_count);
+    atomicAdd(mine + c * 32, 1u);
   };
-  auto count_class = [&](uint32_t c, bool valid) {
-    // lanes of the warp holding class c: one atomic per (warp, class) group
-    uint32_t peers = __ballot_sync(0xffffffffu, valid);
-#pragma unroll
-    for (int b = 0; b < 5; ++b) {
-      const bool bit = (c >> b) & 1u;
-      const uint32_t m = __ballot_sync(0xffffffffu, bit);
-      peers &= bit ? m : ~m;
-    }
-    if (valid && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s_cnt[c], __popc(peers));
-  };
-  const uint64_t stride = (uint64_t)gridDim.x * kDistHistThreads;
-  const uint64_t rounds = ((uint64_t)n + stride - 1) / stride;
-  constexpr int kUnroll = 8;  // loads in flight per thread
-  for (uint64_t r0 = 0; r0 < rounds; r0 += kUnroll) {  // warp-uniform trip count (ballots inside)
-    uint32_t k[kUnroll];
-    bool valid[kUnroll];
+  const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(keys) >> 2) & 3u);
+  uint32_t head = mis ? 4u - mis : 0u;
+  if (head > n) head = n;
+  const uint4* __restrict__ body = reinterpret_cast<const uint4*>(keys + head);
+  const uint64_t nvec = (uint64_t)(n - head) >> 2;
+  const uint32_t tail_start = head + (uint32_t)(nvec << 2);
+  constexpr int kUnroll = 4;
+  const uint64_t stride = (uint64_t)gridDim.x * kDistCountThreads;
+  for (uint64_t v0 = (uint64_t)blockIdx.x * kDistCountThreads + tid; v0 < nvec; v0 += stride * kUnroll) {
+    uint4 q[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      const uint64_t i = (r0 + u) * stride + (uint64_t)blockIdx.x * kDistHistThreads + tid;
-      valid[u] = (r0 + u) < rounds && i < n;
-      k[u] = valid[u] ? LdStream(keys + i) : 0u;
+      const uint64_t v = v0 + (uint64_t)u * stride;
+      q[u] = v < nvec ? __ldcs(body + v) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) count_class(valid[u] ? class_of(k[u]) : 0u, valid[u]);
+    for (int u = 0; u < kUnroll; ++u) {
+      if (v0 + (uint64_t)u * stride < nvec) {
+        count_key(q[u].x); count_key(q[u].y); count_key(q[u].z); count_key(q[u].w);
+      }
+    }
+  }
+  if (blockIdx.x == 0) {  // unaligned head (< 4 keys) and the n % 4 tail
+    if ((uint32_t)tid < head) count_key(keys[tid]);
+    const uint32_t t = tail_start + tid;
+    if (tid < 4 && t < n) count_key(keys[t]);
   }
   __syncthreads();
-  if (tid < (int)(2 * splitter_count + 1) && s_cnt[tid]) atomicAdd(&counts[tid], s_cnt[tid]);
+  // thread (w, c) sums the 32 lane copies of (warp w, class c); one warp-level add per class, one global atomic
+  const uint32_t classes = 2 * splitter_count + 1;
+  for (uint32_t c = warp; c < classes; c += kDistCountThreads / 32) {
+    uint32_t sum = 0;
+    for (int w = 0; w < kDistCountThreads / 32; ++w) sum += s_lane_cnt[w * (kDistClassSlotsForCount * 32) + c * 32 + lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+    if (lane == 0 && sum) atomicAdd(&counts[c], sum);
+  }
 }
 
 // ---- class multi-split ------------------------------------------------------------------------
@@ -320,24 +339,36 @@ DistPartitionKernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t spli
     s_keys[rank[i]] = key[i];
   }
   __syncthreads();
-  // real keys occupy tile-local slots [0, tile_count); recompute the class from the key
-#pragma unroll
-  for (int i = 0; i < kDistPartItems; ++i) {
-    const uint32_t slot = i * kDistPartThreads + tid;
-    if (slot < tile_count) {
-      const uint32_t k = s_keys[slot];
-      const uint32_t c = class_of(k);
-      const uint32_t p = s_gbase[c] + slot;  // class-ordered position among the local keys
-      if (!SCATTER) {
-        out[p] = k;
-      } else {
-        // the keys a tile adds to one class almost always land in one destination; a class that is
-        // split between destinations (ties on a splitter) walks on from there
-        uint32_t j = s_cdest[c];
-#pragma unroll 1
-        while (j + 1 < dest_count && p >= s_dpos[j + 1]) ++j;
-        reinterpret_cast<uint32_t*>(s_dptr[j])[p - s_dpos[j]] = k;
+  // Fused exchange: every class run of the tile goes to its destination's receive buffer in LINE-ALIGNED
+  // warp stores.  A warp-wide store that straddles a 128-byte line of the destination becomes two NVLink
+  // write packets with partial payloads; with slot-linear stores (thread t writes slot t) ncu counted 1.96 GB
+  // on the wire for 1.07 GB of keys (nvltx__bytes, profiles/r02/g_nvlink_partition_probe.txt), i.e. the links
+  // were saturated at 55 % payload.  Here chunk q of a run covers destination words [32 q - a, 32 q - a + 32),
+  // a = misalignment of the run's first word, so every store except the run's ends is one full line.
+  // (The class-ordered local output of vrdxDistCmdPartition is written the same way: full 32-byte sectors.)
+  const uint32_t classes = 2 * splitter_count + 1;
+  for (uint32_t c = 0; c < classes; ++c) {
+    const uint32_t b0 = s_base[c];
+    const uint32_t cnt = (c + 1 < kDistClassSlots ? s_base[c + 1] : tile_count) - b0;  // pads sit in the last slot class
+    if (cnt == 0) continue;
+    const uint32_t p0 = s_gbase[c] + b0;                      // class-ordered position of the run's first key
+    uint32_t j = SCATTER ? s_cdest[c] : 0u;
+    if (SCATTER && j + 1 < dest_count && p0 + cnt > s_dpos[j + 1]) {
+      // the run crosses a destination boundary (ties on a splitter value): element-wise
+      for (uint32_t r = tid; r < cnt; r += kDistPartThreads) {
+        const uint32_t p = p0 + r;
+        uint32_t jj = j;
+        while (jj + 1 < dest_count && p >= s_dpos[jj + 1]) ++jj;
+        reinterpret_cast<uint32_t*>(s_dptr[jj])[p - s_dpos[jj]] = s_keys[b0 + r];
       }
+      continue;
+    }
+    uint32_t* dst = SCATTER ? reinterpret_cast<uint32_t*>(s_dptr[j]) + (p0 - s_dpos[j]) : out + p0;
+    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(dst) >> 2) & 31u;
+    const uint32_t chunks = (cnt + a + 31u) >> 5;
+    for (uint32_t q = warp; q < chunks; q += kWarps) {
+      const uint32_t rel = q * 32u + lane - a;               // wraps below zero for the lanes before the run
+      if (rel < cnt) dst[rel] = s_keys[b0 + rel];
     }
   }
 }

@@ -2,12 +2,12 @@
 
 BASELINE.json configs[4] / SURVEY.md §8(e).  The reference is single-device; this layer is new:
 
-  1. splitters.  Default ("exact"): a 3-level (12/10/10-bit) distributed histogram search finds the
-     key value at every global rank k*N/G (three 4 B/key passes over the local keys, three tiny
-     all-reduces); every rank then receives N/G +- 1 keys for ANY distribution.  Alternative
-     ("sampled"): every rank contributes 2^16 evenly strided keys, the sorted sample gives the
-     splitter values and ONE exact class-count pass (vrdxDistCmdClassCount) gives every (rank,
-     class) size; balance ~1 %.  Measured equal at 2 GPUs (host round trips dominate).  In both, ties on a
+  1. splitters.  "sampled" (what bench.py --gpus N runs): every rank contributes 2^16 keys taken with one
+     common stride, the gathered sample is sorted on the device (by vrdxCmdSort itself) and gives the
+     splitter values; ONE exact class-count pass (vrdxDistCmdClassCount, 4 B/key) gives every (rank,
+     class) size; balance ~1 %.  "exact": a 3-level (12/10/10-bit) distributed histogram search finds the
+     key value at every global rank k*N/G (three 4 B/key passes, three all-reduces, three host round
+     trips); every rank then receives N/G +- 1 keys for ANY distribution.  In both, ties on a
      splitter value (an all-equal input is one big tie) are cut exactly and handed out by source
      rank, which is legal for a keys-only sort because equal keys are indistinguishable;
   2. local multi-split (vrdxDistCmdPartition) into <= 2G-1 classes (open intervals between
@@ -162,6 +162,9 @@ class SharedReceive:
             self.peer_ptrs.append(p.value)
             self._opened.append(p.value)
         self.tensor = torch.as_tensor(_RawCudaArray(self.own_ptr, self.capacity), device=self.device)
+        caps = [torch.empty(1, dtype=torch.int64, device=self.device) for _ in range(world)]
+        dist.all_gather(caps, torch.tensor([self.capacity], dtype=torch.int64, device=self.device), group=group)
+        self.capacities = [int(c.item()) for c in caps]
 
     def close(self):
         torch.cuda.synchronize(self.device)
@@ -282,46 +285,60 @@ def make_plan_exact(backend, keys: torch.Tensor, count: int, group=None) -> Spli
     return _plan_from_class_stats(world, rank, total, targets, v, less_g, eq_g, counts, less_l_all, eq_l_all)
 
 
+def _gather_equal(t: torch.Tensor, world: int, group) -> torch.Tensor:
+    """all-gather of equally sized 1-D tensors -> [world, len(t)]."""
+    out = torch.empty(world * t.numel(), dtype=t.dtype, device=t.device)
+    if t.device.type == "cuda":
+        dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+    else:
+        dist.all_gather(list(out.view(world, -1).unbind(0)), t.contiguous(), group=group)
+    return out.view(world, t.numel())
+
+
 def make_plan_sampled(backend, keys: torch.Tensor, count: int, group=None) -> SplitPlan:
-    """Splitters from a sorted sample (SAMPLES_PER_RANK evenly strided keys per rank), then ONE exact
-    class-count pass over the local keys.  Counts are exact, so the result is exactly sorted and
-    tie classes are still cut exactly; only the balance is approximate (~1 % for uniform keys)."""
+    """Splitters from a sorted sample, then ONE exact class-count pass over the local keys (the default on
+    GPUs: one 4 B/key read and two host round trips instead of three of each).
+
+    Every rank samples its keys with the SAME stride (ceil(largest local count / SAMPLES_PER_RANK), found
+    with one all-reduce), so every sample stands for the same number of keys whatever the local counts
+    are; the gathered samples are sorted on the device by the library's own sort and the splitter of
+    boundary k is the sample at rank k * M / G.  The class counts are exact, so the result is exactly
+    sorted and tie classes are still cut exactly; only the balance is approximate (~1 % for uniform keys)."""
     import numpy as np
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     device = keys.device
     nb = world - 1
     s_n = SAMPLES_PER_RANK
-    # every rank contributes the same number of samples (short ranks repeat / pad with their own keys)
+    cnt_t = torch.tensor([count], dtype=torch.int64, device=device)
+    max_t = cnt_t.clone()
+    dist.all_reduce(max_t, op=dist.ReduceOp.MAX, group=group)
+    stride_t = torch.clamp((max_t + (s_n - 1)) // s_n, min=1)                  # device-side: no host sync here
+    idx = torch.arange(s_n, dtype=torch.int64, device=device) * stride_t
+    valid = idx < cnt_t
     if count > 0:
-        idx = (torch.arange(s_n, device=device, dtype=torch.int64) * count) // s_n
-        sample = keys[:count][idx].contiguous()
-        weight = torch.tensor([count], dtype=torch.int64, device=device)
+        picked = keys[:count][torch.clamp(idx, max=count - 1)]
+        sample = torch.where(valid, picked, torch.full_like(picked, -1))       # pads = 0xFFFFFFFF: they sort last
     else:
-        sample = torch.zeros(s_n, dtype=keys.dtype, device=device)
-        weight = torch.tensor([0], dtype=torch.int64, device=device)
-    gathered = [torch.empty_like(sample) for _ in range(world)]
-    dist.all_gather(gathered, sample, group=group)
-    weights = [torch.empty_like(weight) for _ in range(world)]
-    dist.all_gather(weights, weight, group=group)
-    counts = [int(x) for x in torch.cat(weights).cpu().tolist()]
+        sample = torch.full((s_n,), -1, dtype=keys.dtype, device=device)
+    # message: samples | number of valid samples | local count (two 31-bit halves)
+    tail = torch.stack([valid.sum(), cnt_t[0] & 0x7FFFFFFF, cnt_t[0] >> 31]).to(keys.dtype)
+    pool = _gather_equal(torch.cat([sample, tail]), world, group)                # [world, s_n + 3]
+    samples = pool[:, :s_n].contiguous().view(-1)
+    backend.local_sort(samples, world * s_n, backend.storage_for(world * s_n))  # ascending as unsigned 32-bit
+    m_total = pool[:, s_n].to(torch.int64).sum()
+    qidx = torch.clamp((torch.arange(1, world, dtype=torch.int64, device=device) * m_total) // world, max=world * s_n - 1)
+    picked_q = samples[qidx] if nb else samples[:0]
+    host = torch.cat([pool[:, s_n:].reshape(-1), picked_q]).cpu().tolist()       # host round trip 1
+    counts = [int(host[3 * r + 1]) + (int(host[3 * r + 2]) << 31) for r in range(world)]
     total = sum(counts)
     targets = [k * total // world for k in range(world + 1)]
     if nb == 0 or total == 0:
         return SplitPlan(total, targets, [], [], [[counts[s] if j == 0 else 0 for j in range(world)] for s in range(world)], [0])
-    # weighted sample quantiles on the device: a sample of rank s stands for counts[s] / s_n keys
-    pool = torch.cat(gathered).to(torch.int64) & 0xFFFFFFFF
-    wts = torch.cat([torch.full((s_n,), c / s_n, dtype=torch.float64, device=device) for c in counts])
-    sorted_vals, order = torch.sort(pool)
-    cum = torch.cumsum(wts[order], dim=0)
-    want = torch.tensor(targets[1:world], dtype=torch.float64, device=device)
-    j = torch.searchsorted(cum, want, right=True).clamp(max=pool.numel() - 1)
-    values = [int(x) for x in sorted_vals[j].cpu().tolist()]
+    values = [int(x) & 0xFFFFFFFF for x in host[3 * world:]]
     distinct = sorted(set(values))
     cls = backend.class_count(keys, count, _as_u32_tensor(distinct, device))
-    everyone = [torch.empty_like(cls) for _ in range(world)]
-    dist.all_gather(everyone, cls, group=group)
-    cls_all = torch.stack(everyone).cpu().numpy()                       # [world, 2m+1] exact local class sizes
+    cls_all = _gather_equal(cls, world, group).cpu().numpy()                      # host round trip 2: [world, 2m+1]
     excl = np.concatenate([np.zeros((world, 1), dtype=np.int64), np.cumsum(cls_all, axis=1)[:, :-1]], axis=1)
     less_l_all, eq_l_all = [], []
     for s in range(world):
@@ -364,8 +381,13 @@ def distributed_sort(backend, keys: torch.Tensor, count: int | None = None, grou
     splitters_t = _as_u32_tensor(plan.distinct, device)
     starts_t = _as_u32_tensor(plan.class_starts, device)
     if shared is not None:
-        if recv_count > shared.capacity:
-            raise RuntimeError(f"receive buffer too small: {recv_count} > {shared.capacity}")
+        # the plan is identical on every rank, so every rank checks EVERY destination and they all raise
+        # together: nobody stores past the end of a peer's buffer, nobody waits in the barrier for a
+        # rank that bailed out (capacities are exchanged once, when the buffers are mapped)
+        for j in range(world):
+            need = sum(plan.sizes[s_][j] for s_ in range(world))
+            if need > shared.capacities[j]:
+                raise RuntimeError(f"receive buffer of rank {j} too small: {need} > {shared.capacities[j]}")
         recv = shared.tensor
         # where my keys for destination j start inside j's buffer: after the keys of lower ranks
         first_pos = [0]
