@@ -86,7 +86,7 @@ cudaError_t LaunchUpsweep(cudaStream_t stream, uint32_t grid, const PassArgs& ar
   // the first kernel of a sort (pass 0) is a normal launch: it must wait for the caller's prior work
   return LaunchEx(UpsweepKernel<Cfg::kTile, true>, grid, kUpsweepThreads, 0, stream, pdl && args.pass != 0,
                   args.indirect, args.n_or_max, args.shift, args.mask, args.codec_in, args.keys_in, args.status,
-                  args.status_next, args.hdr, args.ts_end);
+                  args.status_next, args.hdr, args.ts_end, args.ts_start);
 }
 template <int T, int I, bool KV, int M>
 constexpr TileShape MakeShape() {
@@ -299,8 +299,7 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
     } else {
       st.qp = qp;
       st.query = query;
-      StampStartKernel<<<1, 32, 0, stream>>>(st.Written(0), 15);
-      NoteError(sorter, cudaGetLastError());
+      st.Written(0);  // slot 0 and the reset of slots 1..14 are written by the first kernel of the sort (StampStart)
     }
   }
   const uint32_t passes = plan.digits.passes;
@@ -363,9 +362,15 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
   if (!use_rts) {
     // Reset per-sort state inside the stream (reference: vkCmdFillBuffer of the global
     // histogram, h.in:382): header (histograms, tickets) + the pass-0 look-back cells.
-    NoteError(sorter, cudaMemsetAsync(storage, 0,
-                                      lay.status_a_offset + (uint64_t)tiles * kRadix * sizeof(uint32_t),
-                                      stream));
+    const uint64_t reset_bytes = lay.status_a_offset + (uint64_t)tiles * kRadix * sizeof(uint32_t);  // multiple of 16
+    if (st.qp) {
+      const uint64_t blocks = CeilDiv(reset_bytes / 16, (uint64_t)256 * 4);
+      const uint64_t cap = (uint64_t)sorter->sm_count * 4;
+      NoteError(sorter, LaunchEx(ResetKernel, (uint32_t)(blocks < cap ? blocks : cap), 256u, 0, stream, false,
+                                 reinterpret_cast<uint4*>(storage), reset_bytes / 16, st.Slot(0)));
+    } else {
+      NoteError(sorter, cudaMemsetAsync(storage, 0, reset_bytes, stream));
+    }
     ++launches;
     if (n_or_max >= sorter->hist_private_min_count) {
       // lane-private (conflict-free) bins, one 1024-thread CTA per SM
@@ -416,6 +421,9 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
       // spine's segment sums live in the rows after them.  Timestamps fall where the reference puts them.
       args.status = status[0];
       args.status_next = nullptr;
+      if (pass == 0 && st.qp)  // the range upsweep carries no start stamp: an empty reset launch writes slot 0
+        NoteError(sorter, LaunchEx(ResetKernel, 1u, 256u, 0, stream, false, reinterpret_cast<uint4*>(storage), (uint64_t)0,
+                                   st.Slot(0)));
       args.ts_end = st.Written(2 + 3 * pass + 0);
       NoteError(sorter, ek->launch_upsweep(stream, ranges, args, pdl));
       uint32_t* seg = status[0] + (size_t)ranges * kRadix;
@@ -437,6 +445,7 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
       args.status_next = status[1];
       const uint32_t chunks = (uint32_t)CeilDiv(tiles, (uint64_t)kSpineChunk);
       args.ts_end = st.Written(2 + 3 * pass + 0);
+      args.ts_start = pass == 0 ? st.Slot(0) : nullptr;
 #ifdef VRDX_EXPERIMENTS
       if (ek) NoteError(sorter, ek->launch_upsweep(stream, chunks, args, pdl));
       else

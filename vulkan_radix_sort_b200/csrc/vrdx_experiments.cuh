@@ -867,7 +867,9 @@ RangePassKernel(const PassArgs a) {
     }
     __syncthreads();
 
-    TileReorder<Cfg, GENERIC>(sm, key, rank2, row, a.vals_in, tile_start, tile_count, woff, dg);
+    uint32_t val[KV ? IPT : 1];
+    if (kKvEarlyValues) TileLoadValues<Cfg>(val, a.vals_in, tile_start, tile_count, woff);
+    TileReorder<Cfg, GENERIC>(sm, key, rank2, row, a.vals_in, tile_start, tile_count, woff, dg, val);
     // this warp's counter row is free again (only this warp reads its slot bases): zero it for the next tile
     __syncwarp();
     {

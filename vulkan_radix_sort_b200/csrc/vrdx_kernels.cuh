@@ -52,12 +52,26 @@ __device__ __forceinline__ unsigned long long GlobalTimerNs() {
 __device__ __forceinline__ void StampEnd(unsigned long long* slot) {
   if (slot != nullptr && threadIdx.x == 0) atomicMax(slot, GlobalTimerNs());
 }
-// First operation of a sort when a query pool is attached: clears the 15 slots and writes slot 0.
-__global__ void StampStartKernel(unsigned long long* slots, int count) {
-  if (threadIdx.x == 0) {
-    for (int i = 1; i < count; ++i) slots[i] = 0ull;
-    slots[0] = GlobalTimerNs();
+// Start of a sort when a query pool is attached: CTA 0 of the FIRST kernel of the sort clears slots 1..14 and
+// writes slot 0 before it does anything else (no extra launch; the reference records timestamp 0 at the top of
+// gpuSort, h.in:364-366).  Stamps only grow (%globaltimer is monotonic and StampEnd is an atomicMax), so a CTA
+// of the same kernel that finished before CTA 0 got here could at worst be re-stamped by a later one.
+constexpr int kTimestampSlots = 15;
+__device__ __forceinline__ void StampStart(unsigned long long* slots) {
+  if (slots != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    const unsigned long long now = GlobalTimerNs();
+    for (int i = 1; i < kTimestampSlots; ++i) slots[i] = 0ull;
+    slots[0] = now;
+    __threadfence();
   }
+}
+// Onesweep's per-sort reset (header: histograms, tickets; pass-0 look-back cells) as a kernel, so that it can
+// carry the start stamp: with a query pool a sort is one launch shorter than memset + stamp kernel.
+__global__ void __launch_bounds__(256) ResetKernel(uint4* __restrict__ p, uint64_t n16, unsigned long long* slots) {
+  StampStart(slots);
+  GridDepLaunch();
+  for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * 256)
+    p[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 __device__ __forceinline__ uint32_t LaneMaskLt() {
   uint32_t m;
@@ -360,6 +374,7 @@ struct PassArgs {
   const uint32_t* vals_in;
   uint32_t* vals_out;
   unsigned long long* ts_end;  // query-pool slot stamped when this kernel finishes (or nullptr)
+  unsigned long long* ts_start;  // first kernel of a sort with a query pool: slot 0 (StampStart), else nullptr
   // digit of this pass: (word >> shift) & mask (the reference: shift = 8 * pass, mask = 0xFF)
   uint32_t shift, mask;
   KeyCodec codec_in;    // non-zero only on the first pass: caller's key type/order -> sortable word
@@ -711,11 +726,33 @@ __device__ __forceinline__ void TileSlotBases(const TileSmem<Cfg>& sm, const uin
 
 // tile-local reorder through shared memory; values are fetched only now, so they do not occupy
 // registers during the ranking
+// Values of a tile, warp-striped like the keys.
+template <class Cfg>
+__device__ __forceinline__ void TileLoadValues(uint32_t (&val)[Cfg::kKeyValue ? Cfg::kItems : 1], const uint32_t* vals_in,
+                                               uint64_t tile_start, uint32_t tile_count, uint32_t woff) {
+  constexpr int IPT = Cfg::kItems;
+  if (!Cfg::kKeyValue) return;
+  const uint32_t* vin = vals_in + tile_start + woff;
+  if (tile_count == (uint32_t)Cfg::kTile) {
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) val[Cfg::kKeyValue ? i : 0] = LdStream(vin + 32 * i);
+  } else {
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) val[Cfg::kKeyValue ? i : 0] = (woff + 32 * i < tile_count) ? LdStream(vin + 32 * i) : 0u;
+  }
+}
+
+// The values are requested only at the reorder: asking for them right after the ranking (to hide their latency
+// behind the digit scan) keeps 16 more registers live across two barriers and measured 4-8 % slower at every
+// shape (profiles/r02/j_kv_early_values.txt).
+constexpr bool kKvEarlyValues = false;
+
 template <class Cfg, bool GENERIC>
 __device__ __forceinline__ void TileReorder(const TileSmem<Cfg>& sm, const uint32_t (&key)[Cfg::kItems],
                                             const uint32_t (&rank2)[Cfg::kItems / 2], const uint32_t* row,
                                             const uint32_t* vals_in, uint64_t tile_start, uint32_t tile_count, uint32_t woff,
-                                            const PassDigit<GENERIC>& dg) {
+                                            const PassDigit<GENERIC>& dg,
+                                            uint32_t (&val)[Cfg::kKeyValue ? Cfg::kItems : 1]) {
   constexpr int IPT = Cfg::kItems;
   constexpr bool KV = Cfg::kKeyValue;
   char* const keys_b = reinterpret_cast<char*>(sm.keys);
@@ -728,18 +765,10 @@ __device__ __forceinline__ void TileReorder(const TileSmem<Cfg>& sm, const uint3
     if (KV) slot_b[i] = sb;
   }
   if (KV) {
-    const uint32_t* vin = vals_in + tile_start + woff;
-    uint32_t val[IPT];
-    if (tile_count == (uint32_t)Cfg::kTile) {
-#pragma unroll
-      for (int i = 0; i < IPT; ++i) val[i] = LdStream(vin + 32 * i);
-    } else {
-#pragma unroll
-      for (int i = 0; i < IPT; ++i) val[i] = (woff + 32 * i < tile_count) ? LdStream(vin + 32 * i) : 0u;
-    }
+    if (!kKvEarlyValues) TileLoadValues<Cfg>(val, vals_in, tile_start, tile_count, woff);
     char* const vals_b = reinterpret_cast<char*>(sm.vals);
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) *reinterpret_cast<uint32_t*>(vals_b + slot_b[i]) = val[i];
+    for (int i = 0; i < IPT; ++i) *reinterpret_cast<uint32_t*>(vals_b + slot_b[KV ? i : 0]) = val[KV ? i : 0];
   }
 }
 
@@ -870,6 +899,8 @@ PassKernel(const PassArgs a) {
   uint32_t rank2[IPT / 2];
   uint32_t* const row = sm.cnt + warp * kRadix;
   TileRank<Cfg, GENERIC, RANK>(key, rank2, row, full, dg);
+  uint32_t val[KV ? IPT : 1];
+  if (kKvEarlyValues) TileLoadValues<Cfg>(val, a.vals_in, tile_start, tile_count, woff);
   __syncthreads();
 
   uint32_t digit_count = 0, digit_excl = 0;
@@ -902,7 +933,7 @@ PassKernel(const PassArgs a) {
   }
   __syncthreads();
 
-  TileReorder<Cfg, GENERIC>(sm, key, rank2, row, a.vals_in, tile_start, tile_count, woff, dg);
+  TileReorder<Cfg, GENERIC>(sm, key, rank2, row, a.vals_in, tile_start, tile_count, woff, dg, val);
 
   // ---- global offsets of the digit runs ----------------------------------------------------
   if (tid < kRadix) {
@@ -947,12 +978,14 @@ template <int TILE, bool EXCL = false>
 __global__ void __launch_bounds__(kUpsweepThreads)
 UpsweepKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t shift, uint32_t mask,
               const KeyCodec codec_in, const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ tile_hist,
-              uint32_t* __restrict__ chunk_sums, StorageHeader* __restrict__ hdr, unsigned long long* ts_end) {
+              uint32_t* __restrict__ chunk_sums, StorageHeader* __restrict__ hdr, unsigned long long* ts_end,
+              unsigned long long* ts_start) {
   constexpr int THREADS = kUpsweepThreads;
   static_assert(THREADS == kRadix, "one thread per digit");
   static_assert(!EXCL || (uint64_t)(kSpineChunk - 1) * TILE < 65536, "in-chunk prefixes are stored as 16-bit words");
   __shared__ uint32_t h[2][kRadix];
   const int tid = threadIdx.x;
+  StampStart(ts_start);  // non-null only on the first kernel of a sort
   GridDepLaunch();
   const uint32_t n = ResolveCount(indirect, n_or_max);
   const uint32_t tiles = (uint32_t)CeilDiv(n, (uint64_t)TILE);
