@@ -39,7 +39,7 @@ FLAVOURS = {
     "auto": ("AUTO", "AUTO", None),
     # alternate tile shapes compiled into the product library (kKeysShapes / kPairShapes in csrc/vrdx_api.cu)
     "onesweep_256x16": ("ONESWEEP", "DIRECT", (2, 2)),
-    "reduce_then_scan_512x16": ("REDUCE_THEN_SCAN", "DIRECT", (5, 5)),
+    "reduce_then_scan_512x16": ("REDUCE_THEN_SCAN", "DIRECT", (4, 4)),
     # losing variants, only in libraries built with VRDX_EXPERIMENTS=1 (skipped on the product library)
     "x_onesweep_tma_persistent": ("ONESWEEP", "TMA", None),
     "x_reduce_then_scan_tma_persistent": ("REDUCE_THEN_SCAN", "TMA", None),

@@ -24,6 +24,8 @@ for world in (2, 8):
         t = timeit(lambda: b.prefix_histogram(keys, n, shift, bits, pref))
         print(f"world={world} prefix_histogram shift={shift} bits={bits} P={pref.numel()}: {t:.3f} ms  {4*n/t/1e6:.0f} GB/s")
     spl = torch.tensor(bounds, dtype=torch.int64, device="cuda")
+    t = timeit(lambda: b.class_count(keys, n, spl))
+    print(f"world={world} class_count m={nb}: {t:.3f} ms  {4*n/t/1e6:.0f} GB/s")
     k64 = keys.to(torch.int64) & 0xFFFFFFFF
     less = [(k64 < x).sum().item() for x in bounds]; eq = [(k64 == x).sum().item() for x in bounds]
     starts = [0]

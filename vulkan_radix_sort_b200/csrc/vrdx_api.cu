@@ -95,17 +95,18 @@ constexpr TileShape MakeShape() {
                    &LaunchUpsweep<Cfg>};
 }
 
-// Shapes (measured on B200, profiles/r02_shape_sweep.txt).  Index 0 is the onesweep default,
-// kDefault*RtsShape the reduce-then-scan default.
+// Shapes (measured on B200, profiles/r02/n_shape_sweep.txt: 2^28 keys in 3.37 ms with 256 x 20, 3.64 ms with
+// 256 x 16; 2^28 pairs in 5.39 ms with 320 x 20, 5.55 ms with 384 x 16).  Index 0 is the default of both
+// compositions; the others are the alternates the tuning sweeps compare (VrdxCudaSorterOptions::reserved[0..1]).
 static const TileShape kKeysShapes[] = {
-    MakeShape<384, 16, false, 3>(), MakeShape<256, 16, false, 5>(), MakeShape<256, 16, false, 4>(),
-    MakeShape<256, 16, false, 6>(), MakeShape<512, 16, false, 2>(),
+    MakeShape<256, 20, false, 4>(), MakeShape<256, 16, false, 4>(), MakeShape<384, 16, false, 3>(),
+    MakeShape<512, 16, false, 2>(),
 };
 static const TileShape kPairShapes[] = {
-    MakeShape<384, 16, true, 3>(), MakeShape<256, 16, true, 5>(), MakeShape<256, 16, true, 4>(),
-    MakeShape<256, 16, true, 3>(), MakeShape<512, 16, true, 2>(),
+    MakeShape<320, 20, true, 3>(), MakeShape<256, 16, true, 4>(), MakeShape<384, 16, true, 3>(),
+    MakeShape<512, 16, true, 2>(),
 };
-constexpr int kDefaultKeysRtsShape = 2;  // 256 x 16, 4 CTAs/SM: 64 registers, no spills (profiles/r02/b_relaxed_on.txt)
+constexpr int kDefaultKeysRtsShape = 0;
 constexpr int kDefaultPairRtsShape = 0;
 constexpr int kDefaultOnesweepShape = 0;  // keys and pairs
 constexpr int kNumKeysShapes = sizeof(kKeysShapes) / sizeof(kKeysShapes[0]);
@@ -363,13 +364,13 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
     // Reset per-sort state inside the stream (reference: vkCmdFillBuffer of the global
     // histogram, h.in:382): header (histograms, tickets) + the pass-0 look-back cells.
     const uint64_t reset_bytes = lay.status_a_offset + (uint64_t)tiles * kRadix * sizeof(uint32_t);  // multiple of 16
-    if (st.qp) {
+    {
+      // a kernel rather than cudaMemsetAsync: it carries the start stamp, and the histogram kernel launched
+      // next (programmatic dependent launch) counts the caller's keys while it runs
       const uint64_t blocks = CeilDiv(reset_bytes / 16, (uint64_t)256 * 4);
       const uint64_t cap = (uint64_t)sorter->sm_count * 4;
       NoteError(sorter, LaunchEx(ResetKernel, (uint32_t)(blocks < cap ? blocks : cap), 256u, 0, stream, false,
                                  reinterpret_cast<uint4*>(storage), reset_bytes / 16, st.Slot(0)));
-    } else {
-      NoteError(sorter, cudaMemsetAsync(storage, 0, reset_bytes, stream));
     }
     ++launches;
     if (n_or_max >= sorter->hist_private_min_count) {
@@ -377,14 +378,14 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
       uint64_t chunks = CeilDiv(n_or_max, (uint64_t)kHistPrivChunk);
       uint32_t grid = (uint32_t)(chunks < (uint64_t)sorter->sm_count ? chunks : (uint64_t)sorter->sm_count);
       NoteError(sorter, LaunchEx(generic ? HistogramKernelPrivate<true> : HistogramKernelPrivate<false>, grid,
-                                 kHistPrivThreads, kHistPrivSmemBytes, stream, false, (const uint32_t*)keys, indirect,
+                                 kHistPrivThreads, kHistPrivSmemBytes, stream, pdl, (const uint32_t*)keys, indirect,
                                  n_or_max, hdr, st.Written(1), plan.digits));
     } else {
       uint64_t chunks = CeilDiv(n_or_max, (uint64_t)kHistChunk);
       uint64_t cap = (uint64_t)sorter->sm_count * 4;
       uint32_t grid = (uint32_t)(chunks < cap ? (chunks ? chunks : 1) : cap);
       NoteError(sorter, LaunchEx(generic ? HistogramKernel<true> : HistogramKernel<false>, grid, kHistThreads, 0, stream,
-                                 false, (const uint32_t*)keys, indirect, n_or_max, hdr, st.Written(1), plan.digits));
+                                 pdl, (const uint32_t*)keys, indirect, n_or_max, hdr, st.Written(1), plan.digits));
     }
     ++launches;
   } else {
@@ -404,6 +405,7 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
 #ifdef VRDX_EXPERIMENTS
     args.range_tiles = range_tiles;
 #endif
+    args.static_tiles = (!use_rts && tiles <= 2u * (uint32_t)sorter->sm_count) ? 1u : 0u;  // every shape fits >= 2 CTAs/SM
     args.words_only = (!kv && plan.all_bits && sorter->relaxed_equal_low_bits) ? 1u : 0u;
     args.hdr = hdr;
     args.status = status[pass & 1];

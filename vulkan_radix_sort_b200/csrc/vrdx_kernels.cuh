@@ -162,7 +162,6 @@ HistogramKernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ 
   const uint32_t n = ResolveCount(indirect, n_or_max);
 
   for (int i = tid; i < kPasses * kRadix; i += kHistThreads) (&sh[0][0])[i] = 0;
-  if (blockIdx.x == 0 && tid == 0) hdr->element_count[0] = n;
   __syncthreads();
 
   // Peel to 16-byte alignment so the body can use 128-bit loads whatever the caller's offset.
@@ -204,6 +203,10 @@ HistogramKernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ 
   }
   __syncthreads();
 
+  // The header is zeroed by ResetKernel, the launch before this one: with programmatic dependent launch this
+  // kernel has been counting the caller's keys while that one ran, and only waits for it here.
+  GridDepWait();
+  if (blockIdx.x == 0 && tid == 0) hdr->element_count[0] = n;
   uint32_t* gh = &hdr->global_hist[0][0];
   for (int i = tid; i < kPasses * kRadix; i += kHistThreads) {
     uint32_t c = (&sh[0][0])[i];
@@ -277,7 +280,6 @@ HistogramKernelPrivate(const uint32_t* __restrict__ keys, const uint32_t* __rest
     for (int j = 0; j < (int)(kPasses * kRadix * 32 / 4 / kHistPrivThreads); ++j)
       z[j * kHistPrivThreads + tid] = make_uint4(0u, 0u, 0u, 0u);
   }
-  if (blockIdx.x == 0 && tid == 0) hdr->element_count[0] = n;
   __syncthreads();
 
   const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(keys) >> 2) & 3u);
@@ -311,6 +313,8 @@ HistogramKernelPrivate(const uint32_t* __restrict__ keys, const uint32_t* __rest
 
   // one bin per thread: sum its 32 lane copies (rotated start, so the 32 threads of a warp read
   // 32 different banks), then one global atomic per non-empty bin
+  GridDepWait();  // the header is zeroed by the launch before this one (see HistogramKernel)
+  if (blockIdx.x == 0 && tid == 0) hdr->element_count[0] = n;
   uint32_t* gh = &hdr->global_hist[0][0];
   {
     uint32_t c = 0;
@@ -380,6 +384,7 @@ struct PassArgs {
   KeyCodec codec_in;    // non-zero only on the first pass: caller's key type/order -> sortable word
   KeyCodec codec_out;   // non-zero only on the last pass: sortable word -> caller's key type/order
   uint32_t order_free;  // 1: keys-only first pass of a sort over all 32 bits (no order to preserve)
+  uint32_t static_tiles; // onesweep: 1 = the whole grid is co-resident, tile id = blockIdx.x (no ticket round trip)
   uint32_t range_tiles; // RangePassKernel / UpsweepRangeKernel (VRDX_EXPERIMENTS): consecutive tiles per CTA
   uint32_t words_only;  // 1: keys-only sort over all 32 bits (any pass): equal words are indistinguishable, so
                         //    keys that agree in every bit below this pass's digit may swap places (PassKernel)
@@ -873,11 +878,19 @@ PassKernel(const PassArgs a) {
   const bool unordered = (MODE == 0) && order_free;
   const PassDigit<GENERIC> dg = MakePassDigit<Cfg, GENERIC>(a, order_free);
   // Tile ids are handed out in arrival order so that every predecessor a tile may wait on in the
-  // look-back is already resident (forward progress without relying on blockIdx order).
-  if (MODE == 0 && !unordered && tid == 0) sm.misc[8] = atomicAdd(&a.hdr->tickets[pass], 1u);
+  // look-back is already resident (forward progress without relying on blockIdx order).  When the whole
+  // grid is co-resident anyway (small sorts: PassArgs::static_tiles) the ticket's round trip is skipped.
+  const bool ticketed = MODE == 0 && !unordered && a.static_tiles == 0u;
+  if (ticketed && tid == 0) sm.misc[8] = atomicAdd(&a.hdr->tickets[pass], 1u);
+  // Onesweep (small and medium sorts, where the chain of dependent round trips inside a pass is what a sort
+  // costs): the identity flag and the digit's global offset are requested now / with the keys and consumed
+  // later.  Reduce-then-scan (large sorts) keeps them off the register file until they are needed: holding
+  // them across the ranking cost 2.7 % at 2^28 keys (profiles/r02/l_early_loads_ab.txt).
+  constexpr bool kEarly = MODE == 0;
+  const uint32_t identity = kEarly ? a.hdr->pass_identity[pass] : 0u;
   __syncthreads();
 
-  const uint32_t tile = (MODE == 0 && !unordered) ? sm.misc[8] : blockIdx.x;
+  const uint32_t tile = ticketed ? sm.misc[8] : blockIdx.x;
   const uint64_t tile_start = (uint64_t)tile * kTile;
   if (tile_start >= n) return;  // indirect count below max: surplus CTAs retire (upsweep.slang:20-22)
   const uint32_t remaining = (uint32_t)(n - tile_start);
@@ -886,7 +899,7 @@ PassKernel(const PassArgs a) {
 
   if (MODE == 0 && a.status_next != nullptr && tid < kRadix) a.status_next[(size_t)tile * kRadix + tid] = 0;
 
-  if (a.hdr->pass_identity[pass]) {
+  if (!kEarly && a.hdr->pass_identity[pass]) {
     TileCopy<Cfg, GENERIC>(a, tile_start, tile_count, tid, dg);
     StampEnd(a.ts_end);
     return;
@@ -895,6 +908,24 @@ PassKernel(const PassArgs a) {
   uint32_t key[IPT];
   const uint32_t woff = warp * 32 * IPT + lane;
   TileLoadKeys<Cfg, GENERIC>(key, a.keys_in, tile_start, tile_count, woff, dg);
+  // global digit offset of this pass for digit `tid`: needed at the very end, requested with the keys
+  uint32_t digit_base = 0;
+  if (kEarly && tid < kRadix) digit_base = a.hdr->global_hist[pass][tid];
+
+  if (kEarly && identity) {
+    // constant digit: a stable counting sort with one non-empty bucket is a copy (same warp-striped indices out as in)
+    uint32_t cv[KV ? IPT : 1];
+    if (KV) TileLoadValues<Cfg>(cv, a.vals_in, tile_start, tile_count, woff);
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      if (full || woff + 32 * i < tile_count) {
+        a.keys_out[tile_start + woff + 32 * i] = KeyOut(key[i], dg.cout);
+        if (KV) a.vals_out[tile_start + woff + 32 * i] = cv[KV ? i : 0];
+      }
+    }
+    StampEnd(a.ts_end);
+    return;
+  }
 
   uint32_t rank2[IPT / 2];
   uint32_t* const row = sm.cnt + warp * kRadix;
@@ -945,7 +976,8 @@ PassKernel(const PassArgs a) {
       StRelaxed(a.status + (size_t)tile * kRadix + tid, kStatusPrefix | (excl + digit_count));
     }
     // global slot of tile-local slot 0 for this digit (mod 2^32 arithmetic)
-    sm.gbase[tid] = a.hdr->global_hist[pass][tid] + excl - (digit_excl >> 2);
+    if (!kEarly) digit_base = a.hdr->global_hist[pass][tid];
+    sm.gbase[tid] = digit_base + excl - (digit_excl >> 2);
   }
   __syncthreads();
 
