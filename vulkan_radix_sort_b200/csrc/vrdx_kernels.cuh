@@ -5,14 +5,16 @@
 //   src/shader/spine.slang:11-84      exclusive scan over partitions + global histogram scan
 //   src/shader/downsweep.slang:41-224 stable rank, local reorder, scatter (keys / key-value)
 // with a different decomposition:
-//   HistogramKernel   ONE read of the keys builds all four 256-bin digit histograms; the last
-//                     CTA to finish exclusive-scans them in place (no separate spine launch).
-//   OnesweepKernel    one launch per pass: warp-level multi-split ranking (optimistic returning
-//                     shared-memory atomicAdd on warp-private counters + lane-ordered repair of
-//                     collisions), tile-local reorder through shared memory, single-pass
-//                     decoupled look-back across tiles for the digit offsets, run-wise coalesced
-//                     scatter.  Keys and values are two separate
-//                     arrays end to end, as in the reference.
+//   ResetKernel + HistogramKernel[Private]   onesweep: ONE read of the keys builds all four 256-bin digit
+//                     histograms; the last CTA to finish exclusive-scans them in place (no spine launch).
+//   UpsweepKernel + SpineReduce/ApplyKernel  reduce-then-scan: per-tile digit prefixes (16-bit, inside a chunk
+//                     of 8 tiles), chunk prefixes and the global digit offsets of one pass.
+//   PassKernel        one launch per pass, one tile per CTA: warp-level multi-split ranking (returning
+//                     shared-memory atomicAdd on warp-private counters, collisions repaired exactly with a
+//                     REDUX.OR bloom filter + MATCH.ANY on the few colliding lanes), tile-local reorder
+//                     through shared memory, run-wise coalesced scatter; the tile's global offsets come
+//                     from a single-pass decoupled look-back (MODE 0) or from the upsweep tables (MODE 1).
+//                     Keys and values are two separate arrays end to end, as in the reference.
 // Stability: a warp owns 32*IPT consecutive keys and ranks them item by item, lane by lane, so
 // (warp, item, lane) order == index order — the same argument as downsweep.slang:79-80.
 #pragma once
@@ -345,25 +347,21 @@ HistogramKernelPrivate(const uint32_t* __restrict__ keys, const uint32_t* __rest
 }
 
 // ------------------------------------------------------------------------------------------
-// OnesweepKernel — one LSD pass over one tile per CTA.
+// Arguments of one pass (the kernel ABI; reference: the descriptor bindings b0..b6 + the `pass` push
+// constant, h.in:403-440).
 // Algorithmic traffic per pass: 4 B/key read + 4 B/key write (+ 4 + 4 for values).
 //
-// Ranking.  Measured on B200 (tools/microbench_rank.cu; cycles per 32 keys per SM, 32 warps/SM):
-//   hardware MATCH.ANY on an 8-bit digit                                   60.7
+// Ranking primitives measured on B200 (tools/microbench_rank.cu; cycles per 32 keys per SM, 32 warps/SM):
+//   hardware MATCH.ANY on an 8-bit digit, all lanes                        60.7  (1.7 per distinct value)
 //   8-round ballot loop (reference downsweep.slang:92-99; CUB's choice)    28.8
 //   shared-memory atomicOr peer mask + counter cell                        16.5
 //   shared-memory atomicAdd (returning) on a warp-private counter           4.0
-// and the first full kernel built on atomicOr cells was bound by the shared-memory pipe
-// (profiles/: l1tex 77 % busy, 31 wavefronts per 32 keys).  So the rank of a key among equal
-// digits of its warp is computed OPTIMISTICALLY: every lane does one returning atomicAdd(+1) on
-// the warp-private counter of its digit.  A lane that is alone with its digit in this
-// warp-instruction (89 % of lanes on uniform keys) gets its rank straight from the returned
-// value.  Lanes that collided are served by the hardware in an unspecified order, so they are
-// detected (counter read-back: more than one increment landed after my returned value) and
-// REPAIRED in lane order: one shuffle + one ballot per collision group (1.8 groups per 32 uniform
-// keys).  If many lanes collide (low-entropy digits) the repair switches to the fixed 8-round
-// ballot loop.  Ranks are therefore exactly those of a stable counting sort whatever order the
-// hardware serialises colliding atomics in.
+// So the rank of a key among equal digits of its warp is computed OPTIMISTICALLY: every lane does one
+// returning atomicAdd on the warp-private counter of its digit.  A lane that is alone with its digit in this
+// warp-instruction (89 % of lanes on uniform keys) gets its rank straight from the returned value.  Lanes
+// that collided are served by the hardware in an unspecified order, so they are detected (counter
+// read-back) and REPAIRED in lane order (RepairRank below).  Ranks are therefore exactly those of a stable
+// counting sort whatever order the hardware serialises colliding atomics in.
 // ------------------------------------------------------------------------------------------
 struct PassArgs {
   const uint32_t* indirect;   // device count or nullptr
@@ -482,10 +480,10 @@ __device__ __forceinline__ uint32_t LookBack(const uint32_t* status, uint32_t ti
 }
 
 // ------------------------------------------------------------------------------------------
-// PassKernel — the tile kernel of round 2: the same algorithm as OnesweepKernel (one LSD pass over
+// PassKernel — the tile kernel of round 2: the same algorithm as round 1's OnesweepKernel (one LSD pass over
 // one tile per CTA: load, warp-level multi-split ranking, per-digit scan, tile-local reorder
 // through shared memory, run-wise coalesced scatter), rewritten around what the ncu source view
-// of OnesweepKernel showed (profiles/r02_*): 78 warp-instructions and 20.5 shared-memory
+// of the round-1 kernel showed (profiles/r02/a_ncu_source_ops_*): 78 warp-instructions and 20.5 shared-memory
 // wavefronts per 32 keys, the instruction count being the first limiter.
 //   * the digit of the reference plan is one PRMT (byte extract, selector in a register) instead of
 //     shift + mask + scale (the old kernel spent 4-5 instructions per digit use, three uses per key).
