@@ -4,14 +4,15 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vulkan_radix_sort_b200 import Sorter, api
 from vulkan_radix_sort_b200.datagen import make_keys
-flavours = {"onesweep": (1, 1, None), "rts": (2, 1, None), "onesweep_tma": (1, 2, None), "rts_tma": (2, 2, None),
-            "cluster4": (1, 1, (6, 6))}
+flavours = {"onesweep": (1, 1, None), "rts": (2, 1, None), "onesweep_256x16": (1, 1, (2, 2)), "rts_512x16": (2, 1, (4, 4)),
+            # VRDX_EXPERIMENTS builds only:
+            "onesweep_tma": (1, 2, None), "rts_tma": (2, 2, None), "cluster4": (1, 1, (0, 0, 2)), "ranges": (2, 1, (0, 0, 7))}
 only = sys.argv[1:] or list(flavours)
 for name in only:
     algo, load, res = flavours[name]
     s = Sorter(0, algorithm=algo, tile_load=load, reserved=res)
-    for n in (1, 777, 6144, 20011, 70001):
-        for dist in ("uniform", "bits4"):
+    for n in (1, 777, 5120, 6400, 20011, 70001):
+        for dist in ("uniform", "bits4", "sorted"):   # sorted: every warp agrees in the low bits (relaxed ranking)
             k = make_keys(dist, n, 3)
             dk = torch.from_numpy(k.view(np.int32)).cuda()
             dv = torch.arange(n, dtype=torch.int32, device="cuda")

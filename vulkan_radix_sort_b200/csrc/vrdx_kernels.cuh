@@ -748,6 +748,8 @@ __device__ __forceinline__ void TileLoadValues(uint32_t (&val)[Cfg::kKeyValue ? 
 // The values are requested only at the reorder: asking for them right after the ranking (to hide their latency
 // behind the digit scan) keeps 16 more registers live across two barriers and measured 4-8 % slower at every
 // shape (profiles/r02/j_kv_early_values.txt).
+// Staging them with 4-byte cp.async straight into their slots (no registers, no STS) was slower still: 6.04 vs
+// 5.43 ms at 2^28 pairs (profiles/r02/o_kv_cp_async.txt).
 constexpr bool kKvEarlyValues = false;
 
 template <class Cfg, bool GENERIC>
