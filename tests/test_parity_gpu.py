@@ -328,6 +328,52 @@ def test_launch_count_reported(sorter):
     torch.cuda.synchronize()
 
 
+# ------------------------------------------------------------------ reduce-then-scan: block-free tiles
+
+def _rts_sorter(reserved=None):
+    from vulkan_radix_sort_b200 import Sorter
+    return Sorter(0, algorithm=api.VRDX_CUDA_ALGORITHM_REDUCE_THEN_SCAN, reserved=reserved)
+
+
+@pytest.mark.parametrize("two_runs", ["-1", "0", "1"], ids=["two_runs_auto", "two_runs_never", "two_runs_always"])
+@pytest.mark.parametrize("reserved", [None, (2, 2), (4, 4)], ids=["256x20", "256x16", "512x16"])
+def test_block_free_tiles_one_run_two_runs_three_runs(oracle, reserved, two_runs, monkeypatch):
+    """Keys-only reduce-then-scan tiles whose keys agree below the digit (one run), or are exactly two such
+    runs, take TileBlockFree (csrc/vrdx_kernels.cuh); tiles of three and more runs rank stably.  The crafted
+    inputs put all three kinds of tile into passes 1, 2 and 3; the result must equal the oracle's bit for bit."""
+    # which passes run the two-run kernel flavours is decided from the count (run length on uniform keys); the
+    # developer switch forces them on / off so that every pass of the crafted inputs meets both flavours
+    monkeypatch.setenv("VRDX_TWO_RUNS", two_runs)
+    s = _rts_sorter(reserved)
+    tile = int(s.properties.keysTileSize)
+    rng = np.random.default_rng(77)
+    cases = []
+    for n in ((1 << 21) + 777, 3 << 20, 40 * tile, 40 * tile + 1):
+        cases.append(("uniform", rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)))
+        for m in (1, 2, 3, 40, 300, 5000):  # distinct values of the low 16 bits: runs of ~n/m keys in pass 2
+            low = rng.choice(1 << 16, size=m, replace=False).astype(np.uint32)
+            k = low[rng.integers(0, m, n)] | (rng.integers(0, 1 << 16, n, dtype=np.uint32) << np.uint32(16))
+            cases.append((f"low16x{m}", k.astype(np.uint32)))
+        for m in (2, 7, 200):  # ... of the low 24 bits: long runs in pass 3 as well
+            low = rng.choice(1 << 24, size=m, replace=False).astype(np.uint32)
+            k = low[rng.integers(0, m, n)] | (rng.integers(0, 1 << 8, n, dtype=np.uint32) << np.uint32(24))
+            cases.append((f"low24x{m}", k.astype(np.uint32)))
+        # runs of exactly tile, tile/2 and tile+1 keys below the second digit: boundaries on and off the tile edges
+        for run in (tile, tile // 2, tile + 1, 2 * tile - 1):
+            k = ((np.arange(n, dtype=np.uint64) // run) % 256).astype(np.uint32) | \
+                (rng.integers(0, 1 << 24, n, dtype=np.uint32) << np.uint32(8))
+            cases.append((f"run{run}", rng.permutation(k)))
+    for name, k in cases:
+        assert np.array_equal(gpu_sort_keys(s, k), oracle.sort_keys(k)), (name, len(k))
+    # the same inputs as key-value sorts never take the block-free path; spot-check that the tables still serve them
+    name, k = cases[3]
+    v = np.arange(len(k), dtype=np.uint32)
+    ok, ov = gpu_sort_kv(s, k, v)
+    ek, ev = oracle.sort_key_value(k, v)
+    assert np.array_equal(ok, ek) and np.array_equal(ov, ev), name
+    s.close()
+
+
 # ------------------------------------------------------------------ BASELINE.json full sizes
 
 def _property_check(oracle, k_in, k_out, v_out=None):

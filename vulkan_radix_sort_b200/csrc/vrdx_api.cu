@@ -71,22 +71,35 @@ cudaError_t PrepareShape(int* ctas_per_sm) {
   opt_in(PassKernel<Cfg, 1, false>);
   opt_in(PassKernel<Cfg, 0, true>);
   opt_in(PassKernel<Cfg, 1, true>);
+  if constexpr (!Cfg::kKeyValue) {
+    opt_in(PassKernel<Cfg, 1, false, VRDX_RANK, true>);
+    opt_in(PassKernel<Cfg, 1, true, VRDX_RANK, true>);
+  }
   if (e != cudaSuccess) return e;
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, PassKernel<Cfg, 1, false>, Cfg::kThreads,
                                                        Cfg::kSmemBytes);
 }
+// two: the instantiations whose two-run tiles are block-free too (keys-only reduce-then-scan; PassArgs::two_runs)
 template <class Cfg>
 cudaError_t LaunchPass(cudaStream_t stream, uint32_t grid, const PassArgs& args, int mode, bool generic, bool pdl) {
   void (*k)(const PassArgs) = mode == 0 ? (generic ? PassKernel<Cfg, 0, true> : PassKernel<Cfg, 0, false>)
                                         : (generic ? PassKernel<Cfg, 1, true> : PassKernel<Cfg, 1, false>);
+  if constexpr (!Cfg::kKeyValue) {
+    if (mode == 1 && args.two_runs)
+      k = generic ? PassKernel<Cfg, 1, true, VRDX_RANK, true> : PassKernel<Cfg, 1, false, VRDX_RANK, true>;
+  }
   return LaunchEx(k, grid, Cfg::kThreads, Cfg::kSmemBytes, stream, pdl, args);
 }
+// Bits below the digit of this pass when keys that agree in them may swap places (PassArgs::words_only, see
+// MakePassDigit in the kernels), else all 32 bits.
+inline uint32_t LowMask(const PassArgs& a) { return a.words_only ? ((1u << a.shift) - 1u) : 0xFFFFFFFFu; }
 template <class Cfg>
 cudaError_t LaunchUpsweep(cudaStream_t stream, uint32_t grid, const PassArgs& args, bool pdl) {
   // the first kernel of a sort (pass 0) is a normal launch: it must wait for the caller's prior work
-  return LaunchEx(UpsweepKernel<Cfg::kTile, true>, grid, kUpsweepThreads, 0, stream, pdl && args.pass != 0,
-                  args.indirect, args.n_or_max, args.shift, args.mask, args.codec_in, args.keys_in, args.status,
-                  args.status_next, args.hdr, args.ts_end, args.ts_start);
+  return LaunchEx(args.two_runs ? UpsweepKernel<Cfg::kTile, true, true> : UpsweepKernel<Cfg::kTile, true, false>, grid,
+                  kUpsweepThreads, 0, stream, pdl && args.pass != 0, args.indirect, args.n_or_max, args.shift, args.mask,
+                  args.codec_in, args.keys_in, args.status, args.status_next, args.hdr, args.ts_end, args.ts_start,
+                  args.tile_flags, LowMask(args));
 }
 template <int T, int I, bool KV, int M>
 constexpr TileShape MakeShape() {
@@ -136,6 +149,8 @@ struct VrdxSorter_T {
   int keys_rts_ctas = 1, pair_rts_ctas = 1;               // co-resident CTAs per SM of the scatter kernels
   bool pdl = true;                                        // programmatic dependent launch between our own kernels
   bool relaxed_equal_low_bits = true;                     // PassArgs::words_only (developer switch VRDX_RELAXED=0)
+  int two_runs = -1;                                      // PassArgs::two_runs: -1 by run length (default), 0 never,
+                                                          // 1 in every pass above the first (developer switch VRDX_TWO_RUNS)
   uint32_t hist_private_min_count = kHistPrivateMinCount;  // lane-private histogram bins from this count up
 #ifdef VRDX_EXPERIMENTS
   ExperimentSelection exp;
@@ -227,6 +242,29 @@ struct Stamps {
     qp->recorded[query + i] = 1;
   }
 };
+
+// Spine of one reduce-then-scan pass over `rows` chunk rows; returns the number of launches.  The segments of the
+// fused kernel wait for each other, so its grid must be co-resident: 128 tiny CTAs, at most 4 per SM.
+uint32_t SpineGrid(const VrdxSorter_T* s, uint32_t rows) {
+  uint32_t cap = (uint32_t)kSpineSegments;
+  if ((uint32_t)s->sm_count * 4u < cap) cap = (uint32_t)s->sm_count * 4u;
+  return rows < cap ? (rows ? rows : 1u) : cap;
+}
+uint32_t LaunchSpine(VrdxSorter s, cudaStream_t stream, bool pdl, uint32_t grid, const uint32_t* indirect, uint32_t n_or_max,
+                     uint32_t tile_size, uint32_t fixed_rows, uint32_t pass, uint32_t* rows, uint32_t* seg, StorageHeader* hdr,
+                     unsigned long long* ts_end) {
+#if VRDX_SPINE_FUSED
+  NoteError(s, LaunchEx(SpineKernel, grid, (uint32_t)kRadix, 0, stream, pdl, indirect, n_or_max, tile_size, fixed_rows, pass,
+                        rows, seg, hdr, ts_end));
+  return 1;
+#else
+  NoteError(s, LaunchEx(SpineReduceKernel, grid, (uint32_t)kRadix, 0, stream, pdl, indirect, n_or_max, tile_size, fixed_rows,
+                        pass, (const uint32_t*)rows, seg, hdr));
+  NoteError(s, LaunchEx(SpineApplyKernel, grid, (uint32_t)kRadix, 0, stream, pdl, indirect, n_or_max, tile_size, fixed_rows,
+                        rows, (const uint32_t*)seg, ts_end));
+  return 2;
+#endif
+}
 
 // What a sort compares: the reference's plan (uint32 ascending, four 8-bit digits) or the plan
 // of a VrdxCudaSortKeyInfo (key type / order as a codec, bit sub-range as fewer, narrower digits).
@@ -429,14 +467,12 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
       args.ts_end = st.Written(2 + 3 * pass + 0);
       NoteError(sorter, ek->launch_upsweep(stream, ranges, args, pdl));
       uint32_t* seg = status[0] + (size_t)ranges * kRadix;
-      const uint32_t seg_grid = ranges < (uint32_t)kSpineSegments ? ranges : (uint32_t)kSpineSegments;
-      NoteError(sorter, LaunchEx(SpineReduceKernel, seg_grid, (uint32_t)kRadix, 0, stream, pdl, indirect, n_or_max,
-                                 tile_size, ranges, pass, (const uint32_t*)status[0], seg, hdr));
-      NoteError(sorter, LaunchEx(SpineApplyKernel, seg_grid, (uint32_t)kRadix, 0, stream, pdl, indirect, n_or_max,
-                                 tile_size, ranges, status[0], (const uint32_t*)seg, st.Written(2 + 3 * pass + 1)));
+      const uint32_t seg_grid = SpineGrid(sorter, ranges);
+      launches += LaunchSpine(sorter, stream, pdl, seg_grid, indirect, n_or_max, tile_size, ranges, pass, status[0], seg, hdr,
+                              st.Written(2 + 3 * pass + 1));
       args.ts_end = st.Written(2 + 3 * pass + 2);
       NoteError(sorter, ek->launch(stream, ranges, args, 1, pdl));
-      launches += 4;
+      launches += 2;
       continue;
     }
 #endif
@@ -446,6 +482,18 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
       args.status = status[0];
       args.status_next = status[1];
       const uint32_t chunks = (uint32_t)CeilDiv(tiles, (uint64_t)kSpineChunk);
+      // keys-only sorts over all 32 bits: one flag byte per tile after the spine's rows (chunk prefixes, segment sums)
+      // (only where keys that agree below the digit may swap places: the flags rely on the input of a pass being
+      // sorted by exactly those bits)
+      if (args.words_only) {
+        args.tile_flags = reinterpret_cast<uint8_t*>(status[1] + ((size_t)chunks + kSpineSegments + 1) * kRadix);
+        // Tiles of exactly two runs are worth their own kernel flavour only where they are common: on uniform keys
+        // the runs of pass p are count / 2^shift keys long, and between half a tile and three tiles that makes
+        // more than a third of the tiles two-run (2^28 keys: pass 2, runs of 4096; 2^29: pass 2, runs of 8192).
+        const uint64_t run = (uint64_t)n_or_max >> args.shift;
+        args.two_runs = (pass > 0 && (sorter->two_runs < 0 ? (2 * run >= tile_size && run <= 3ull * tile_size)
+                                                           : sorter->two_runs != 0)) ? 1u : 0u;
+      }
       args.ts_end = st.Written(2 + 3 * pass + 0);
       args.ts_start = pass == 0 ? st.Slot(0) : nullptr;
 #ifdef VRDX_EXPERIMENTS
@@ -455,19 +503,16 @@ void EnqueueSort(VkCommandBuffer commandBuffer, VrdxSorter sorter, uint32_t n_or
       NoteError(sorter, shape.launch_upsweep(stream, chunks, args, pdl));
       // spine scratch: chunk prefixes occupy rows [0, chunks) of status B, segment sums the rows after them
       uint32_t* seg = status[1] + (size_t)chunks * kRadix;
-      const uint32_t seg_grid = chunks < (uint32_t)kSpineSegments ? (chunks ? chunks : 1u) : (uint32_t)kSpineSegments;
-      NoteError(sorter, LaunchEx(SpineReduceKernel, seg_grid, (uint32_t)kRadix, 0, stream, pdl, indirect,
-                                 n_or_max, tile_size, 0u, pass, (const uint32_t*)status[1], seg, hdr));
-      NoteError(sorter, LaunchEx(SpineApplyKernel, seg_grid, (uint32_t)kRadix, 0, stream, pdl, indirect,
-                                 n_or_max, tile_size, 0u, status[1], (const uint32_t*)seg,
-                                 st.Written(2 + 3 * pass + 1)));
+      const uint32_t seg_grid = SpineGrid(sorter, chunks);
+      launches += LaunchSpine(sorter, stream, pdl, seg_grid, indirect, n_or_max, tile_size, 0u, pass, status[1], seg, hdr,
+                              st.Written(2 + 3 * pass + 1));
       args.ts_end = st.Written(2 + 3 * pass + 2);
 #ifdef VRDX_EXPERIMENTS
       if (ek) NoteError(sorter, ek->launch(stream, pass_grid, args, 1, pdl));
       else
 #endif
       NoteError(sorter, shape.launch_pass(stream, tiles, args, 1, generic, pdl));
-      launches += 4;
+      launches += 2;
       continue;
     }
     // One fused kernel per pass: the reference's upsweep and spine slots collapse onto its start.
@@ -584,6 +629,7 @@ VkResult vrdxCudaCreateSorter(const VrdxSorterCreateInfo* pCreateInfo,
   if (const char* e = getenv("VRDX_ALGORITHM")) s->algorithm = (VrdxCudaAlgorithm)atoi(e);
   if (const char* e = getenv("VRDX_PDL")) s->pdl = atoi(e) != 0;
   if (const char* e = getenv("VRDX_RELAXED")) s->relaxed_equal_low_bits = atoi(e) != 0;
+  if (const char* e = getenv("VRDX_TWO_RUNS")) s->two_runs = atoi(e);
   if (const char* e = getenv("VRDX_HIST_PRIVATE_MIN")) s->hist_private_min_count = (uint32_t)strtoul(e, nullptr, 10);
 #ifdef VRDX_EXPERIMENTS
   if (!PrepareExperiments(&s->exp, experiment, tile_load, s->sm_count)) {

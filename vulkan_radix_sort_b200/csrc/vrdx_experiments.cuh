@@ -922,7 +922,7 @@ UpsweepRangeKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uin
   RangeOf(tiles, range_tiles, blockIdx.x, first, count);
   h[tid] = 0;
   GridDepWait();
-  if (blockIdx.x == 0 && tid == 0) hdr->hist_blocks_done = 0;  // counter of this pass's SpineReduceKernel
+  ResetSpineState(hdr, tid);
   __syncthreads();
   constexpr int kIters = (TILE + THREADS - 1) / THREADS;
   for (uint32_t tile = first; tile < first + count; ++tile) {

@@ -386,8 +386,13 @@ struct PassArgs {
   uint32_t range_tiles; // RangePassKernel / UpsweepRangeKernel (VRDX_EXPERIMENTS): consecutive tiles per CTA
   uint32_t words_only;  // 1: keys-only sort over all 32 bits (any pass): equal words are indistinguishable, so
                         //    keys that agree in every bit below this pass's digit may swap places (PassKernel)
+  uint8_t* tile_flags;  // reduce-then-scan, keys-only: tile_flags[tile] = 1 when all keys of a (full) tile agree in the
+                        //    bits below this pass's digit — written by UpsweepKernel, read by PassKernel<.., 1>
+                        //    (TileBlockFree); nullptr: not kept (key-value sorts)
+  uint32_t two_runs;    // 1: this pass runs the kernel flavours that also detect / take tiles of exactly two runs
 };
 
+constexpr uint8_t kTileOneRun = 1, kTileTwoRuns = 2;  // PassArgs::tile_flags
 constexpr int kSpineChunk = (int)kSpineChunkTiles;  // reduce-then-scan: tiles per upsweep CTA / spine chunk
 constexpr int kRepairBallotThreshold = 12;  // colliding lanes above which the 8-round ballot loop is cheaper
 
@@ -501,12 +506,21 @@ __device__ __forceinline__ uint32_t LookBack(const uint32_t* status, uint32_t ti
 // MODE 0: onesweep (tickets + decoupled look-back)   MODE 1: reduce-then-scan scatter pass.
 // GENERIC = false: the reference's digit plan (shift = 8 * pass, mask = 0xFF, identity codec);
 // GENERIC = true: digit and codec from PassArgs (vrdxCudaCmdSortEx).
+// TWO (MODE 1, keys-only): tiles the upsweep flagged kTileTwoRuns take TileBlockFree as well.  A separate
+// instantiation, launched only for passes in which such tiles are likely (EnqueueSort): with both block-free
+// flavours compiled in, the one-run tiles of the other passes ran 7 % slower (profiles/r02/q_block_free_tiles.txt).
 // ------------------------------------------------------------------------------------------
 #ifndef VRDX_RANK_PIPELINE
 #define VRDX_RANK_PIPELINE 1  // 1: the read-back / repair of item i is issued after the atomic of item i + 1
 #endif
 #ifndef VRDX_RANK_SYNCWARP
 #define VRDX_RANK_SYNCWARP 1  // 1: __syncwarp() between a warp's atomics and the counter read-back; 0: compiler fence only
+#endif
+#ifndef VRDX_SPINE_FUSED
+#define VRDX_SPINE_FUSED 1  // 1: SpineKernel (one launch per pass); 0: SpineReduceKernel + SpineApplyKernel
+#endif
+#ifndef VRDX_BLOCK_FREE
+#define VRDX_BLOCK_FREE 1  // 1: reduce-then-scan keys-only tiles the upsweep flagged take TileBlockFree
 #endif
 #ifndef VRDX_RANK
 #define VRDX_RANK 1  // 0: shuffle + ballot loop per collision group; 1: bloom + MATCH.ANY; 2: REDUX.MIN loop
@@ -833,6 +847,65 @@ __device__ __forceinline__ void TileCopy(const PassArgs& a, uint64_t tile_start,
   }
 }
 
+// Reduce-then-scan, keys-only, a full tile whose keys all agree in the bits below the digit (always in pass 0;
+// pass 1 of a large sort: a tile lies inside one run of pass 0's order): ANY bijection of the tile's keys onto the
+// slots of their digit runs gives the same final result (TileRank explains why), and the tile's digit counts are
+// already in the upsweep's table.  So the slot bases are computed first (while the keys are still in flight) and
+// every key takes its final tile slot with ONE returning shared-memory atomicAdd on a block-wide cursor row and
+// is stored there: 2 digit-indexed shared-memory accesses per key instead of 3 (atomic, slot base, store), no
+// per-warp rows to sum, two barriers fewer.
+// TWO (tile flag kTileTwoRuns): the tile is two runs of keys that agree below the digit (it straddles one boundary
+// of the previous passes' order; `first` = the tile's first key).  Keys of the first run must precede keys of the
+// second inside every digit: the first run takes its slots from the FRONT of the digit's range (ascending cursor),
+// the second from the BACK (descending cursor) — the two meet exactly, because the range has as many slots as
+// the digit has keys.
+template <class Cfg, bool GENERIC, bool TWO>
+__device__ __forceinline__ void TileBlockFree(const PassArgs& a, const TileSmem<Cfg>& sm, const uint32_t (&key)[Cfg::kItems],
+                                              uint32_t tile, int tid, const PassDigit<GENERIC>& dg, uint32_t first) {
+  constexpr int IPT = Cfg::kItems;
+  const int lane = tid & 31, warp = tid >> 5;
+  uint32_t count = 0, incl = 0, gb = 0;
+  if (tid < kRadix) {
+    const uint16_t* t16 = reinterpret_cast<const uint16_t*>(a.status);
+    const uint32_t before = (tile % kSpineChunk) ? t16[(size_t)(tile - 1) * kRadix + tid] : 0u;
+    count = (t16[(size_t)tile * kRadix + tid] - before) & 0xFFFFu;
+    gb = a.status_next[(size_t)(tile / kSpineChunk) * kRadix + tid] + before + a.hdr->global_hist[a.pass][tid];
+    incl = WarpInclusiveScan(count, lane);
+    if (lane == 31) sm.misc[warp] = incl;
+  }
+  __syncthreads();
+  if (tid < kRadix) {
+    uint32_t excl = incl - count;
+#pragma unroll
+    for (int w = 0; w < kRadix / 32; ++w) excl += (w < warp) ? sm.misc[w] : 0u;
+    sm.cnt[tid] = excl << 2;      // byte offset of the digit's next free tile slot
+    if (TWO) sm.cnt[kRadix + tid] = (excl + count) << 2;  // ... and of the end of its range
+    sm.gbase[tid] = gb - excl;    // global slot of tile-local slot 0 for this digit (mod 2^32 arithmetic)
+  }
+  __syncthreads();
+  char* const keys_b = reinterpret_cast<char*>(sm.keys);
+  uint32_t slot2[IPT / 2];
+  auto claim = [&](uint32_t k) -> uint32_t {
+    const uint32_t d = DigitOf<GENERIC>(k, dg.shift, dg.mask);
+    if (!TWO) return atomicAdd(sm.cnt + d, 4u);
+    const bool second = ((k ^ first) & dg.lowmask) != 0u;
+    const uint32_t r = atomicAdd(sm.cnt + (second ? kRadix : 0) + d, second ? 0xFFFFFFFCu : 4u);
+    return second ? r - 4u : r;
+  };
+#pragma unroll
+  for (int i = 0; i < IPT; i += 2) {
+    const uint32_t s0 = claim(key[i]);
+    const uint32_t s1 = claim(key[i + 1]);
+    slot2[i / 2] = __byte_perm(s0, s1, 0x5410);
+  }
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    const uint32_t sb = (i & 1) ? (slot2[i / 2] >> 16) : (slot2[i / 2] & 0xFFFFu);
+    *reinterpret_cast<uint32_t*>(keys_b + sb) = key[i];
+  }
+  __syncthreads();
+}
+
 template <class Cfg, bool GENERIC>
 __device__ __forceinline__ PassDigit<GENERIC> MakePassDigit(const PassArgs& a, bool order_free) {
   PassDigit<GENERIC> dg;
@@ -847,7 +920,7 @@ __device__ __forceinline__ PassDigit<GENERIC> MakePassDigit(const PassArgs& a, b
   return dg;
 }
 
-template <class Cfg, int MODE, bool GENERIC, int RANK = VRDX_RANK>
+template <class Cfg, int MODE, bool GENERIC, int RANK = VRDX_RANK, bool TWO = false>
 __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinCtas)
 PassKernel(const PassArgs a) {
   constexpr int THREADS = Cfg::kThreads;
@@ -899,6 +972,10 @@ PassKernel(const PassArgs a) {
 
   if (MODE == 0 && a.status_next != nullptr && tid < kRadix) a.status_next[(size_t)tile * kRadix + tid] = 0;
 
+  // reduce-then-scan, keys-only: did the upsweep find the keys of this tile to be one or two runs below the digit?
+  // (TileBlockFree.)  The flag travels with the identity word: one round trip before the keys are requested.
+  uint32_t block_free = 0;
+  if (MODE == 1 && !KV && VRDX_BLOCK_FREE && a.tile_flags != nullptr) block_free = a.tile_flags[tile];
   if (!kEarly && a.hdr->pass_identity[pass]) {
     TileCopy<Cfg, GENERIC>(a, tile_start, tile_count, tid, dg);
     StampEnd(a.ts_end);
@@ -907,6 +984,17 @@ PassKernel(const PassArgs a) {
 
   uint32_t key[IPT];
   const uint32_t woff = warp * 32 * IPT + lane;
+  if (MODE == 1 && !KV && VRDX_BLOCK_FREE && (TWO ? block_free != 0u : block_free == kTileOneRun) && full) {
+    // (its own copy of the key loads: the flag is tested BEFORE they are issued, so that the table loads of
+    // TileBlockFree go out right behind them instead of waiting for the keys' scoreboard;
+    // profiles/r02/q_block_free_tiles.txt)
+    TileLoadKeys<Cfg, GENERIC>(key, a.keys_in, tile_start, tile_count, woff, dg);
+    if (!TWO || block_free == kTileOneRun) TileBlockFree<Cfg, GENERIC, false>(a, sm, key, tile, tid, dg, 0u);
+    else TileBlockFree<Cfg, GENERIC, true>(a, sm, key, tile, tid, dg, KeyIn(a.keys_in[tile_start], dg.cin));
+    TileScatter<Cfg, GENERIC>(sm, a.keys_out, a.vals_out, tile_count, tid, dg);
+    StampEnd(a.ts_end);
+    return;
+  }
   TileLoadKeys<Cfg, GENERIC>(key, a.keys_in, tile_start, tile_count, woff, dg);
   // global digit offset of this pass for digit `tid`: needed at the very end, requested with the keys
   uint32_t digit_base = 0;
@@ -959,7 +1047,7 @@ PassKernel(const PassArgs a) {
     } else {
       // reduce-then-scan: scanned chunk prefix + this tile's exclusive prefix inside its chunk
       look_s[0] = a.status_next[(size_t)(tile / kSpineChunk) * kRadix + tid] +
-                  reinterpret_cast<const uint16_t*>(a.status)[(size_t)tile * kRadix + tid];
+                  ((tile % kSpineChunk) ? reinterpret_cast<const uint16_t*>(a.status)[(size_t)(tile - 1) * kRadix + tid] : 0u);
     }
   }
   __syncthreads();
@@ -1002,19 +1090,32 @@ PassKernel(const PassArgs a) {
 // ------------------------------------------------------------------------------------------
 constexpr int kUpsweepThreads = 256;
 
-// EXCL: tile_hist is a table of 16-bit words, tile_hist[tile][d] = number of digit-d keys in the EARLIER
-// tiles of the same chunk (< kSpineChunk * TILE <= 2^16; what PassKernel<.., 1> adds to the chunk prefix):
-// half the bytes of the reference's partHist (h.in:353-362).  !EXCL (round-1 kernels, VRDX_EXPERIMENTS):
-// 32-bit words holding the tile's own count.
-template <int TILE, bool EXCL = false>
+// First CTA of an upsweep (after its GridDepWait: the previous pass has finished, this pass's spine has not begun):
+// the spine's per-pass state.
+__device__ __forceinline__ void ResetSpineState(StorageHeader* hdr, int tid) {
+  if (blockIdx.x != 0) return;
+  if (tid == 0) hdr->hist_blocks_done = 0;  // last-block-done counter (two-kernel spine)
+  if (tid < (int)kSpineSegmentRows) hdr->spine_flags[tid] = 0;
+}
+
+// INCL: tile_hist is a table of 16-bit words, tile_hist[tile][d] = number of digit-d keys in this tile and the
+// EARLIER tiles of the same chunk (<= kSpineChunk * TILE < 2^16).  PassKernel<.., 1> adds the row of the tile
+// before it (nothing for the first tile of a chunk) to the chunk prefix; the difference of the two rows is the
+// tile's own digit count, known before the tile is ranked (TileBlockFree).  Half the bytes of the reference's
+// partHist (h.in:353-362).  !INCL (round-1 kernels, VRDX_EXPERIMENTS): 32-bit words holding the tile's own count.
+// tile_flags (keys-only sorts over all 32 bits, else nullptr): tile_flags[tile] = kTileOneRun when the tile is full
+// and all its keys agree in the bits of `lowmask` (the bits below this pass's digit), kTileTwoRuns when they take
+// two values there (the first key's, then the last key's).
+template <int TILE, bool INCL = false, bool TWO = false>
 __global__ void __launch_bounds__(kUpsweepThreads)
 UpsweepKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t shift, uint32_t mask,
               const KeyCodec codec_in, const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ tile_hist,
               uint32_t* __restrict__ chunk_sums, StorageHeader* __restrict__ hdr, unsigned long long* ts_end,
-              unsigned long long* ts_start) {
+              unsigned long long* ts_start, uint8_t* __restrict__ tile_flags = nullptr, uint32_t lowmask = 0xFFFFFFFFu) {
   constexpr int THREADS = kUpsweepThreads;
   static_assert(THREADS == kRadix, "one thread per digit");
-  static_assert(!EXCL || (uint64_t)(kSpineChunk - 1) * TILE < 65536, "in-chunk prefixes are stored as 16-bit words");
+  // (the last row of a chunk may wrap at 2^16: it is only ever used in a difference mod 2^16, never as a prefix)
+  static_assert(!INCL || (uint64_t)(kSpineChunk - 1) * TILE < 65536, "in-chunk prefixes are stored as 16-bit words");
   __shared__ uint32_t h[2][kRadix];
   const int tid = threadIdx.x;
   StampStart(ts_start);  // non-null only on the first kernel of a sort
@@ -1025,7 +1126,7 @@ UpsweepKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t
   h[0][tid] = 0;
   h[1][tid] = 0;
   GridDepWait();
-  if (blockIdx.x == 0 && tid == 0) hdr->hist_blocks_done = 0;  // counter of this pass's SpineScanKernel
+  ResetSpineState(hdr, tid);
   if (first >= tiles) return;
   const uint32_t last = first + kSpineChunk < tiles ? first + kSpineChunk : tiles;
   constexpr int kIters = (TILE + THREADS - 1) / THREADS;
@@ -1038,11 +1139,38 @@ UpsweepKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t
     const uint32_t tile_count = remaining < (uint32_t)TILE ? remaining : (uint32_t)TILE;
     const uint32_t* kin = keys_in + tile_start;
     uint32_t k[kIters];
+    // Tile flag (keys-only sorts over all 32 bits; see the header comment).  The input of this pass is sorted by the
+    // bits of lowmask (the invariant of an LSD sort; lowmask == 0 in the first pass), so the tile is ONE run iff
+    // its first and last key agree there — two broadcast loads, nothing per key.  TWO runs need every key looked
+    // at (does it agree with the first or with the last key?); that loop runs only when two more samples say so.
+    int flag = 0;        // uniform over the CTA
+    uint32_t stray = 0;  // non-zero: some key differs (below the digit) from both the first and the last key
     if (tile_count == (uint32_t)TILE) {
 #pragma unroll
       for (int i = 0; i < kIters; ++i) k[i] = LdStream(kin + i * THREADS + tid);
+      uint32_t l0 = 0, ll = 0;
+      bool maybe_two = false;
+      if (tile_flags != nullptr) {
+        l0 = kin[0] & lowmask;  // (flags are kept for passes whose codec_in is the identity, or with lowmask == 0)
+        ll = kin[TILE - 1] & lowmask;
+        flag = l0 == ll ? kTileOneRun : 0;
+        if (TWO && l0 != ll) {
+          const uint32_t la = kin[TILE / 3] & lowmask, lb = kin[2 * (TILE / 3)] & lowmask;
+          maybe_two = (la == l0 || la == ll) && (lb == l0 || lb == ll) && !(la == ll && lb == l0);
+        }
+      }
+      if (maybe_two) {
 #pragma unroll
-      for (int i = 0; i < kIters; ++i) atomicAdd(&hh[(KeyIn(k[i], codec_in) >> shift) & mask], 1u);
+        for (int i = 0; i < kIters; ++i) {
+          const uint32_t kk = KeyIn(k[i], codec_in);
+          atomicAdd(&hh[(kk >> shift) & mask], 1u);
+          stray |= min((kk & lowmask) ^ l0, (kk & lowmask) ^ ll);
+        }
+        flag = kTileTwoRuns;  // unless a stray key turns up (barrier below)
+      } else {
+#pragma unroll
+        for (int i = 0; i < kIters; ++i) atomicAdd(&hh[(KeyIn(k[i], codec_in) >> shift) & mask], 1u);
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < kIters; ++i) {
@@ -1050,12 +1178,14 @@ UpsweepKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t
         if (idx < tile_count) atomicAdd(&hh[(KeyIn(LdStream(kin + idx), codec_in) >> shift) & mask], 1u);
       }
     }
-    __syncthreads();  // one barrier per tile: the two histograms alternate
+    // one barrier per tile: the two histograms alternate
+    const int no_stray = __syncthreads_and(stray == 0u);
     const uint32_t c = hh[tid];
     hh[tid] = 0;      // ready for tile + 2 (the next tile uses the other buffer; barrier above orders it)
-    if (EXCL) reinterpret_cast<uint16_t*>(tile_hist)[(size_t)tile * kRadix + tid] = (uint16_t)chunk_acc;
-    else tile_hist[(size_t)tile * kRadix + tid] = c;
     chunk_acc += c;
+    if (INCL) reinterpret_cast<uint16_t*>(tile_hist)[(size_t)tile * kRadix + tid] = (uint16_t)chunk_acc;
+    else tile_hist[(size_t)tile * kRadix + tid] = c;
+    if (INCL && tile_flags != nullptr && tid == 0) tile_flags[tile] = (uint8_t)(no_stray ? flag : 0);
   }
   chunk_sums[(size_t)blockIdx.x * kRadix + tid] = chunk_acc;
   StampEnd(ts_end);
@@ -1150,6 +1280,75 @@ SpineApplyKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint3
       if (b0 + j < r1) chunk_sums[(size_t)(b0 + j) * kRadix + tid] = run;
       run += v[j];
     }
+  }
+  StampEnd(ts_end);
+}
+
+// SpineKernel — the two kernels above as one (what ships; VRDX_SPINE_FUSED=0 keeps the pair for A/B).  The grid is
+// at most kSpineSegments (128) small CTAs, all co-resident on a 148-SM part, so a CTA may wait for the others:
+//   1. CTA s sums the rows of segment s, publishes seg[s][256] and raises spine_flags[s]
+//   2. waits for the flags of segments < s and sums their rows: the segment's exclusive prefix (no chain: every
+//      CTA needs only the SUMS of its predecessors, which all appear one round trip after the slowest read)
+//   3. rewrites its rows (still in L2) as exclusive prefixes; the last CTA also turns the per-digit totals into
+//      the global digit offsets and the identity flag
+// One launch and ~one kernel drain less per pass than the pair: 2^28 keys 26 -> ~10 us per pass.
+__global__ void __launch_bounds__(kRadix)
+SpineKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t tile_size, uint32_t fixed_rows, uint32_t pass,
+            uint32_t* __restrict__ chunk_sums, uint32_t* __restrict__ seg, StorageHeader* __restrict__ hdr,
+            unsigned long long* ts_end) {
+  __shared__ uint32_t s_warp[kRadix / 32];
+  GridDepLaunch();
+  GridDepWait();
+  const uint32_t n = ResolveCount(indirect, n_or_max);
+  uint32_t chunks, rows_per;
+  SpineGeometry(n, tile_size, fixed_rows, chunks, rows_per);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t r0 = blockIdx.x * rows_per;
+  const uint32_t r1 = r0 + rows_per < chunks ? r0 + rows_per : chunks;
+  uint32_t sum = 0;
+#pragma unroll 16
+  for (uint32_t r = r0; r < r1; ++r) sum += __ldcg(chunk_sums + (size_t)r * kRadix + tid);
+  StRelaxed(seg + (size_t)blockIdx.x * kRadix + tid, sum);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) StRelaxed(&hdr->spine_flags[blockIdx.x], 1u);
+  // every predecessor is resident (grid <= 128 CTAs of 256 threads and no shared memory to speak of)
+  if (warp == 0)
+    for (uint32_t s0 = lane; s0 < blockIdx.x; s0 += 32)
+      while (LdRelaxed(&hdr->spine_flags[s0]) == 0u) {}
+  __threadfence();
+  __syncthreads();
+  uint32_t run = 0;
+  for (uint32_t s0 = 0; s0 < blockIdx.x; s0 += 32) {  // 32 rows in flight per round trip
+    uint32_t v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = (s0 + j < blockIdx.x) ? LdRelaxed(seg + (size_t)(s0 + j) * kRadix + tid) : 0u;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) run += v[j];
+  }
+  for (uint32_t b0 = r0; b0 < r1; b0 += 16) {  // 16 rows in flight; loads never wait behind the aliasing stores
+    uint32_t v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = (b0 + j < r1) ? __ldcg(chunk_sums + (size_t)(b0 + j) * kRadix + tid) : 0u;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (b0 + j < r1) chunk_sums[(size_t)(b0 + j) * kRadix + tid] = run;
+      run += v[j];
+    }
+  }
+  if (blockIdx.x == gridDim.x - 1) {
+    // run == number of keys with digit `tid`: exclusive scan over digits -> global digit offsets
+    const uint32_t incl = WarpInclusiveScan(run, lane);
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t prefix = 0;
+#pragma unroll
+    for (int w = 0; w < kRadix / 32; ++w) prefix += (w < warp) ? s_warp[w] : 0u;
+    hdr->global_hist[pass][tid] = prefix + incl - run;
+    if (tid == 0 && pass == 0) hdr->element_count[0] = n;
+    // one digit holds every key: this pass is the identity permutation (the scatter tiles just copy)
+    const int any = __syncthreads_or(run == n && n != 0);
+    if (tid == 0) hdr->pass_identity[pass] = any ? 1u : 0u;
   }
   StampEnd(ts_end);
 }
