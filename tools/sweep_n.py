@@ -10,7 +10,10 @@ host = torch.from_numpy(make_keys("uniform", 1 << 28, 1).view(np.int32))
 src_all = host.cuda()
 vals_all = torch.arange(1 << 28, dtype=torch.int32, device="cuda")
 import math
-for n in [1 << 18, 1 << 20, 1 << 21, 3 << 20, 1 << 22, 3 << 21, 1 << 23, 3 << 22, 1 << 24, 3 << 23, 1 << 25, 1 << 26]:
+sizes = [1 << 18, 1 << 20, 1 << 21, 3 << 20, 1 << 22, 3 << 21, 1 << 23, 3 << 22, 1 << 24, 3 << 23, 1 << 25, 1 << 26]
+if len(sys.argv) > 1:
+    sizes = [int(eval(a)) for a in sys.argv[1:]]
+for n in sizes:
     line = f"{n:9d} (2^{math.log2(n):.2f})"
     for kv in (False, True):
         for name, s in sorters.items():

@@ -519,6 +519,9 @@ __device__ __forceinline__ uint32_t LookBack(const uint32_t* status, uint32_t ti
 #ifndef VRDX_SPINE_FUSED
 #define VRDX_SPINE_FUSED 1  // 1: SpineKernel (one launch per pass); 0: SpineReduceKernel + SpineApplyKernel
 #endif
+#ifndef VRDX_BLOCK_FREE_LDG128
+#define VRDX_BLOCK_FREE_LDG128 1  // 1: block-free tiles load their keys with 128-bit loads
+#endif
 #ifndef VRDX_BLOCK_FREE
 #define VRDX_BLOCK_FREE 1  // 1: reduce-then-scan keys-only tiles the upsweep flagged take TileBlockFree
 #endif
@@ -988,6 +991,22 @@ PassKernel(const PassArgs a) {
     // (its own copy of the key loads: the flag is tested BEFORE they are issued, so that the table loads of
     // TileBlockFree go out right behind them instead of waiting for the keys' scoreboard;
     // profiles/r02/q_block_free_tiles.txt)
+#if VRDX_BLOCK_FREE_LDG128
+    // The order of a block-free tile's keys does not matter, so a thread takes four consecutive keys per 128-bit
+    // load (the survey's "128-bit loads + in-register transpose" without the transpose): same wavefronts, 15
+    // load instructions fewer per thread; 2^28 keys 3.28 -> 3.22 ms (profiles/r02/r_ldg128_block_free.txt).
+    if ((reinterpret_cast<uintptr_t>(a.keys_in) & 15u) == 0u && IPT % 4 == 0) {
+      const uint4* k4 = reinterpret_cast<const uint4*>(a.keys_in + tile_start) + tid;
+#pragma unroll
+      for (int i = 0; i < IPT / 4; ++i) {
+        const uint4 q = __ldcs(k4 + i * THREADS);
+        key[4 * i + 0] = KeyIn(q.x, dg.cin);
+        key[4 * i + 1] = KeyIn(q.y, dg.cin);
+        key[4 * i + 2] = KeyIn(q.z, dg.cin);
+        key[4 * i + 3] = KeyIn(q.w, dg.cin);
+      }
+    } else
+#endif
     TileLoadKeys<Cfg, GENERIC>(key, a.keys_in, tile_start, tile_count, woff, dg);
     if (!TWO || block_free == kTileOneRun) TileBlockFree<Cfg, GENERIC, false>(a, sm, key, tile, tid, dg, 0u);
     else TileBlockFree<Cfg, GENERIC, true>(a, sm, key, tile, tid, dg, KeyIn(a.keys_in[tile_start], dg.cin));
@@ -1138,7 +1157,6 @@ UpsweepKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t
     const uint32_t remaining = (uint32_t)(n - tile_start);
     const uint32_t tile_count = remaining < (uint32_t)TILE ? remaining : (uint32_t)TILE;
     const uint32_t* kin = keys_in + tile_start;
-    uint32_t k[kIters];
     // Tile flag (keys-only sorts over all 32 bits; see the header comment).  The input of this pass is sorted by the
     // bits of lowmask (the invariant of an LSD sort; lowmask == 0 in the first pass), so the tile is ONE run iff
     // its first and last key agree there — two broadcast loads, nothing per key.  TWO runs need every key looked
@@ -1146,8 +1164,31 @@ UpsweepKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t
     int flag = 0;        // uniform over the CTA
     uint32_t stray = 0;  // non-zero: some key differs (below the digit) from both the first and the last key
     if (tile_count == (uint32_t)TILE) {
+      // Counting does not care which thread sees which key: 128-bit loads (a thread takes four consecutive keys)
+      // when the caller's pointer allows it.  (With 25 scalar loads per thread the compiler interleaved loads and
+      // atomics to save registers and the 6400-key instantiation ran at 230 instead of 180 us per 2^28 keys.)
+      constexpr int kVec = TILE / (4 * THREADS);          // full rounds of one uint4 per thread
+      constexpr int kVecTail = (TILE % (4 * THREADS)) / 4;  // threads that take one more
+      static_assert(TILE % 4 == 0, "tiles are whole uint4s");
+      uint32_t k[4 * (kVec + 1) > kIters ? 4 * (kVec + 1) : kIters];
+      int have = kIters;
+      if ((reinterpret_cast<uintptr_t>(keys_in) & 15u) == 0u) {
+        const uint4* k4 = reinterpret_cast<const uint4*>(kin);
 #pragma unroll
-      for (int i = 0; i < kIters; ++i) k[i] = LdStream(kin + i * THREADS + tid);
+        for (int i = 0; i < kVec; ++i) {
+          const uint4 q = __ldcs(k4 + i * THREADS + tid);
+          k[4 * i + 0] = q.x; k[4 * i + 1] = q.y; k[4 * i + 2] = q.z; k[4 * i + 3] = q.w;
+        }
+        have = 4 * kVec;
+        if (kVecTail != 0 && tid < kVecTail) {
+          const uint4 q = __ldcs(k4 + kVec * THREADS + tid);
+          k[4 * kVec + 0] = q.x; k[4 * kVec + 1] = q.y; k[4 * kVec + 2] = q.z; k[4 * kVec + 3] = q.w;
+          have = 4 * kVec + 4;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < kIters; ++i) k[i] = LdStream(kin + i * THREADS + tid);
+      }
       uint32_t l0 = 0, ll = 0;
       bool maybe_two = false;
       if (tile_flags != nullptr) {
@@ -1159,17 +1200,21 @@ UpsweepKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t
           maybe_two = (la == l0 || la == ll) && (lb == l0 || lb == ll) && !(la == ll && lb == l0);
         }
       }
+      constexpr int kHeld = (int)(sizeof(k) / sizeof(k[0]));
       if (maybe_two) {
 #pragma unroll
-        for (int i = 0; i < kIters; ++i) {
-          const uint32_t kk = KeyIn(k[i], codec_in);
-          atomicAdd(&hh[(kk >> shift) & mask], 1u);
-          stray |= min((kk & lowmask) ^ l0, (kk & lowmask) ^ ll);
+        for (int i = 0; i < kHeld; ++i) {
+          if (i < have) {
+            const uint32_t kk = KeyIn(k[i], codec_in);
+            atomicAdd(&hh[(kk >> shift) & mask], 1u);
+            stray |= min((kk & lowmask) ^ l0, (kk & lowmask) ^ ll);
+          }
         }
         flag = kTileTwoRuns;  // unless a stray key turns up (barrier below)
       } else {
 #pragma unroll
-        for (int i = 0; i < kIters; ++i) atomicAdd(&hh[(KeyIn(k[i], codec_in) >> shift) & mask], 1u);
+        for (int i = 0; i < kHeld; ++i)
+          if (i < have) atomicAdd(&hh[(KeyIn(k[i], codec_in) >> shift) & mask], 1u);
       }
     } else {
 #pragma unroll
