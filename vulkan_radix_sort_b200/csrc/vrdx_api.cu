@@ -124,11 +124,13 @@ constexpr int kDefaultPairRtsShape = 0;
 constexpr int kDefaultOnesweepShape = 0;  // keys and pairs
 constexpr int kNumKeysShapes = sizeof(kKeysShapes) / sizeof(kKeysShapes[0]);
 constexpr int kNumPairShapes = sizeof(kPairShapes) / sizeof(kPairShapes[0]);
-// Smallest tile of any compiled shape: sizes the per-tile tables whichever shape runs.
+// Smallest tile of any compiled shape: sizes the per-tile tables of the VRDX_EXPERIMENTS build, whichever shape runs.
 constexpr uint32_t kMinTile = 4096;  // 256 x 16
-// AUTO: reduce-then-scan at and above this count, onesweep (fewer launches) below it.
-constexpr uint32_t kAutoRtsThresholdKeys = 3u << 23;   // measured crossovers (profiles/r01_sweep_n_final.txt):
-constexpr uint32_t kAutoRtsThresholdPairs = 3u << 24;  // keys-only ~2^24.6, key-value ~2^25.6
+// AUTO: reduce-then-scan at and above this count, onesweep (fewer launches) below it.  Measured crossovers
+// (profiles/r02/s_sweep_n_auto_thresholds.txt): keys-only 2^25 (block-free tiles and the 128-bit upsweep moved it down
+// from 2^25.6), key-value ~2^27.5 (the two compositions are within 1 % of each other from 2^27 up).
+constexpr uint32_t kAutoRtsThresholdKeys = 1u << 25;
+constexpr uint32_t kAutoRtsThresholdPairs = 1u << 27;
 // the conflict-free histogram kernel needs enough keys to fill one 1024-thread CTA per SM
 constexpr uint32_t kHistPrivateMinCount = 1u << 21;
 
@@ -169,10 +171,16 @@ static StorageLayout SorterLayout(const VrdxSorter_T* s, uint64_t max_count, boo
   return ComputeLayout(max_count, kMinTile, ~0ull, true);  // the round-1 kernels keep 32-bit per-tile rows everywhere
 #else
   // (a NULL sorter — legal for the pure size query — is answered like the default, AUTO, sorter)
-  if (s && s->algorithm == VRDX_CUDA_ALGORITHM_ONESWEEP) return ComputeLayout(max_count, kMinTile, ~0ull);
-  if (s && s->algorithm == VRDX_CUDA_ALGORITHM_REDUCE_THEN_SCAN) return ComputeLayout(max_count, kMinTile, 0);
+  // One table row per tile of the smaller of the two tile shapes this sorter uses for this kind of sort.
+  const TileShape* shapes = key_value ? kPairShapes : kKeysShapes;
+  const uint32_t t_one = shapes[s ? (key_value ? s->pair_shape : s->keys_shape) : kDefaultOnesweepShape].tile;
+  const uint32_t t_rts = shapes[s ? (key_value ? s->pair_rts_shape : s->keys_rts_shape)
+                                  : (key_value ? kDefaultPairRtsShape : kDefaultKeysRtsShape)].tile;
+  const uint32_t min_tile = t_one < t_rts ? t_one : t_rts;
+  if (s && s->algorithm == VRDX_CUDA_ALGORITHM_ONESWEEP) return ComputeLayout(max_count, min_tile, ~0ull);
+  if (s && s->algorithm == VRDX_CUDA_ALGORITHM_REDUCE_THEN_SCAN) return ComputeLayout(max_count, min_tile, 0);
   // AUTO: a count below the crossover of this kind of sort may run onesweep
-  return ComputeLayout(max_count, kMinTile, key_value ? kAutoRtsThresholdPairs : kAutoRtsThresholdKeys);
+  return ComputeLayout(max_count, min_tile, key_value ? kAutoRtsThresholdPairs : kAutoRtsThresholdKeys);
 #endif
 }
 
