@@ -124,8 +124,10 @@ constexpr int kDefaultPairRtsShape = 0;
 constexpr int kDefaultOnesweepShape = 0;  // keys and pairs
 constexpr int kNumKeysShapes = sizeof(kKeysShapes) / sizeof(kKeysShapes[0]);
 constexpr int kNumPairShapes = sizeof(kPairShapes) / sizeof(kPairShapes[0]);
+#ifdef VRDX_EXPERIMENTS
 // Smallest tile of any compiled shape: sizes the per-tile tables of the VRDX_EXPERIMENTS build, whichever shape runs.
 constexpr uint32_t kMinTile = 4096;  // 256 x 16
+#endif
 // AUTO: reduce-then-scan at and above this count, onesweep (fewer launches) below it.  Measured crossovers
 // (profiles/r02/s_sweep_n_auto_thresholds.txt): keys-only 2^25 (block-free tiles and the 128-bit upsweep moved it down
 // from 2^25.6), key-value ~2^27.5 (the two compositions are within 1 % of each other from 2^27 up).

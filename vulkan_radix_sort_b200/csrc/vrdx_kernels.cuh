@@ -519,6 +519,9 @@ __device__ __forceinline__ uint32_t LookBack(const uint32_t* status, uint32_t ti
 #ifndef VRDX_SPINE_FUSED
 #define VRDX_SPINE_FUSED 1  // 1: SpineKernel (one launch per pass); 0: SpineReduceKernel + SpineApplyKernel
 #endif
+#ifndef VRDX_COUNT_FIRST
+#define VRDX_COUNT_FIRST 0  // 1: onesweep tiles count their digits and publish the aggregate before ranking (A/B)
+#endif
 #ifndef VRDX_BLOCK_FREE_LDG128
 #define VRDX_BLOCK_FREE_LDG128 1  // 1: block-free tiles load their keys with 128-bit loads
 #endif
@@ -946,6 +949,7 @@ PassKernel(const PassArgs a) {
     uint4* z = reinterpret_cast<uint4*>(sm.cnt);
 #pragma unroll
     for (int j = tid; j < kWarps * kRadix / 4; j += THREADS) z[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (MODE == 0 && VRDX_COUNT_FIRST && tid < kRadix / 4) reinterpret_cast<uint4*>(sm.gbase)[tid] = make_uint4(0u, 0u, 0u, 0u);
   }
   GridDepWait();  // everything below reads what the previous kernel of this sort wrote
   // keys-only first pass of a sort over all 32 bits: no earlier order to preserve (see TileRank), so an
@@ -1034,6 +1038,23 @@ PassKernel(const PassArgs a) {
     return;
   }
 
+#if VRDX_COUNT_FIRST
+  // Onesweep, ordered passes: count the tile's digits BEFORE ranking (one non-returning shared-memory atomic per key
+  // on a block-wide row) and publish the aggregate now, so that the successors' look-back — and this tile's own,
+  // consumed after the reorder — overlaps the whole ranking instead of only the reorder.
+  const bool count_first = MODE == 0 && !unordered;
+  if (count_first) {
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) atomicAdd(sm.gbase + DigitOf<GENERIC>(key[i], dg.shift, dg.mask), 1u);
+    __syncthreads();
+    if (tid < kRadix) {
+      const uint32_t c = sm.gbase[tid] - (((uint32_t)tid == dg.mask) ? ((uint32_t)kTile - tile_count) : 0u);
+      StRelaxed(a.status + (size_t)tile * kRadix + tid, (tile == 0 ? kStatusPrefix : kStatusAggregate) | c);
+    }
+  }
+#else
+  constexpr bool count_first = false;
+#endif
   uint32_t rank2[IPT / 2];
   uint32_t* const row = sm.cnt + warp * kRadix;
   TileRank<Cfg, GENERIC, RANK>(key, rank2, row, full, dg);
@@ -1045,7 +1066,7 @@ PassKernel(const PassArgs a) {
   uint32_t wcount[kWarps];
   if (tid < kRadix) {
     TileDigitSums<Cfg>(sm, wcount, digit_count, digit_excl, tile_count, dg.mask, tid);
-    if (MODE == 0 && !unordered)
+    if (MODE == 0 && !unordered && !count_first)
       StRelaxed(a.status + (size_t)tile * kRadix + tid,
                 (tile == 0 ? kStatusPrefix : kStatusAggregate) | digit_count);
   }
