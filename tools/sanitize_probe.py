@@ -27,5 +27,16 @@ for name in only:
             c = int(cnt.item())
             got = dk.cpu().numpy().view(np.uint32)
             assert np.array_equal(got[:c], np.sort(k[:c], kind="stable")), (name, n, dist)
+    if algo == 2:
+        # block-free tiles (keys-only reduce-then-scan): run VRDX_TWO_RUNS=1 to cover the two-run flavours too;
+        # few distinct values below the second / third digit give tiles of one, two and more runs in passes 1 and 2
+        rng = np.random.default_rng(5)
+        for n in (20011, 70001):
+            for m in (2, 3, 9):
+                low = rng.choice(1 << 16, size=m, replace=False).astype(np.uint32)
+                k = (low[rng.integers(0, m, n)] | (rng.integers(0, 1 << 16, n, dtype=np.uint32) << np.uint32(16))).astype(np.uint32)
+                kk = torch.from_numpy(k.view(np.int32)).cuda()
+                s.sort(kk)
+                assert np.array_equal(kk.cpu().numpy().view(np.uint32), np.sort(k)), (name, n, m, 'block-free')
     s.close()
     print("ok", name, flush=True)

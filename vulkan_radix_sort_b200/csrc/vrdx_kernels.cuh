@@ -1134,7 +1134,7 @@ constexpr int kUpsweepThreads = 256;
 // the spine's per-pass state.
 __device__ __forceinline__ void ResetSpineState(StorageHeader* hdr, int tid) {
   if (blockIdx.x != 0) return;
-  if (tid == 0) hdr->hist_blocks_done = 0;  // last-block-done counter (two-kernel spine)
+  if (tid == 0) hdr->hist_blocks_done = 0;  // segment ticket of SpineKernel / last-block-done counter of the two-kernel spine
   if (tid < (int)kSpineSegmentRows) hdr->spine_flags[tid] = 0;
 }
 
@@ -1363,32 +1363,38 @@ SpineKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t t
             uint32_t* __restrict__ chunk_sums, uint32_t* __restrict__ seg, StorageHeader* __restrict__ hdr,
             unsigned long long* ts_end) {
   __shared__ uint32_t s_warp[kRadix / 32];
+  __shared__ uint32_t s_seg;
   GridDepLaunch();
   GridDepWait();
   const uint32_t n = ResolveCount(indirect, n_or_max);
   uint32_t chunks, rows_per;
   SpineGeometry(n, tile_size, fixed_rows, chunks, rows_per);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t r0 = blockIdx.x * rows_per;
+  // segment ids are handed out in arrival order (like the onesweep tiles): every segment a CTA waits for below
+  // belongs to a CTA that is already running, whatever order the hardware starts the grid in
+  if (tid == 0) s_seg = atomicAdd(&hdr->hist_blocks_done, 1u);
+  __syncthreads();
+  const uint32_t seg_id = s_seg;
+  const uint32_t r0 = seg_id * rows_per;
   const uint32_t r1 = r0 + rows_per < chunks ? r0 + rows_per : chunks;
   uint32_t sum = 0;
 #pragma unroll 16
   for (uint32_t r = r0; r < r1; ++r) sum += __ldcg(chunk_sums + (size_t)r * kRadix + tid);
-  StRelaxed(seg + (size_t)blockIdx.x * kRadix + tid, sum);
+  StRelaxed(seg + (size_t)seg_id * kRadix + tid, sum);
   __threadfence();
   __syncthreads();
-  if (tid == 0) StRelaxed(&hdr->spine_flags[blockIdx.x], 1u);
+  if (tid == 0) StRelaxed(&hdr->spine_flags[seg_id], 1u);
   // every predecessor is resident (grid <= 128 CTAs of 256 threads and no shared memory to speak of)
   if (warp == 0)
-    for (uint32_t s0 = lane; s0 < blockIdx.x; s0 += 32)
+    for (uint32_t s0 = lane; s0 < seg_id; s0 += 32)
       while (LdRelaxed(&hdr->spine_flags[s0]) == 0u) {}
   __threadfence();
   __syncthreads();
   uint32_t run = 0;
-  for (uint32_t s0 = 0; s0 < blockIdx.x; s0 += 32) {  // 32 rows in flight per round trip
+  for (uint32_t s0 = 0; s0 < seg_id; s0 += 32) {  // 32 rows in flight per round trip
     uint32_t v[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = (s0 + j < blockIdx.x) ? LdRelaxed(seg + (size_t)(s0 + j) * kRadix + tid) : 0u;
+    for (int j = 0; j < 32; ++j) v[j] = (s0 + j < seg_id) ? LdRelaxed(seg + (size_t)(s0 + j) * kRadix + tid) : 0u;
 #pragma unroll
     for (int j = 0; j < 32; ++j) run += v[j];
   }
@@ -1402,7 +1408,7 @@ SpineKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t t
       run += v[j];
     }
   }
-  if (blockIdx.x == gridDim.x - 1) {
+  if (seg_id == gridDim.x - 1) {
     // run == number of keys with digit `tid`: exclusive scan over digits -> global digit offsets
     const uint32_t incl = WarpInclusiveScan(run, lane);
     if (lane == 31) s_warp[warp] = incl;
