@@ -13,14 +13,15 @@ run() {  # name, kernel regex, launches to skip, env, command...
   rm -f $O/$name.ncu-rep $O/$name.src.csv
   grep -E "kernel:|time_duration|dram__bytes_(read|write).sum \[" $O/$name.txt | head -4
 }
-KEYS=2**28 run k_scatter_keys_pass0_relaxed PassKernel 0 "X=1" python tools/ncu_one.py 28 keys 1
-KEYS=2**28 run k_scatter_keys_pass2 PassKernel 2 "X=1" python tools/ncu_one.py 28 keys 1
+KEYS=2**28 run k_scatter_keys_pass0_blockfree PassKernel 0 "X=1" python tools/ncu_one.py 28 keys 1
+KEYS=2**28 run k_scatter_keys_pass2_two_runs PassKernel 2 "X=1" python tools/ncu_one.py 28 keys 1
 KEYS=2**28 run k_scatter_keys_pass3_stable PassKernel 3 "X=1" python tools/ncu_one.py 28 keys 1
-KEYS=2**28 run k_scatter_kv PassKernel 1 "X=1" python tools/ncu_one.py 28 kv 1
+KEYS=2**28 run k_scatter_kv PassKernel 1 "VRDX_ALGORITHM=2" python tools/ncu_one.py 28 kv 1
 KEYS=2**28 run k_upsweep UpsweepKernel 1 "X=1" python tools/ncu_one.py 28 keys 1
-KEYS=2**28 run k_spine_reduce SpineReduce 1 "X=1" python tools/ncu_one.py 28 keys 1
-KEYS=2**28 run k_spine_apply SpineApply 1 "X=1" python tools/ncu_one.py 28 keys 1
+KEYS=2**28 run k_upsweep_kv UpsweepKernel 1 "VRDX_ALGORITHM=2" python tools/ncu_one.py 28 kv 1
+KEYS=2**28 run k_spine SpineKernel 1 "X=1" python tools/ncu_one.py 28 keys 1
 KEYS=2**24 run k_hist_private HistogramKernelPrivate 0 "VRDX_ALGORITHM=1" python tools/ncu_one.py 24 keys 1
 KEYS=2**24 run k_onesweep_lookback PassKernel 1 "VRDX_ALGORITHM=1" python tools/ncu_one.py 24 keys 1
+[ -n "$SKIP_DIST" ] && exit 0
 KEYS=2**29 run k_dist_class_count DistClassCount 0 "X=1" python tools/dist_kernels_bench.py 29
 KEYS=2**29 run k_dist_partition DistPartition 1 "X=1" python tools/dist_kernels_bench.py 29
