@@ -54,6 +54,28 @@ def test_key_types_and_order_keys_and_pairs(sorter, oracle, n, key_type, descend
     assert np.array_equal(gk, ek) and np.array_equal(gv, ev)
 
 
+@pytest.mark.parametrize("two_runs", ["-1", "1"], ids=["two_runs_auto", "two_runs_always"])
+@pytest.mark.parametrize("key_type,descending", [("int32", False), ("float32", True), ("uint32", True)])
+def test_block_free_tiles_with_key_codecs(oracle, key_type, descending, two_runs, monkeypatch):
+    """Keys-only reduce-then-scan over all 32 bits of typed / descending keys: the GENERIC instantiations of the
+    block-free tile paths (csrc/vrdx_kernels.cuh TileBlockFree; one-run tiles in pass 0, one- and two-run tiles in
+    pass 1 at this size, and — forced — in every later pass of the low-entropy input)."""
+    from vulkan_radix_sort_b200 import Sorter
+    monkeypatch.setenv("VRDX_TWO_RUNS", two_runs)
+    s = Sorter(0, algorithm=api.VRDX_CUDA_ALGORITHM_REDUCE_THEN_SCAN)
+    kt = KEY_TYPES[key_type]
+    n = (1 << 21) + 777
+    rng = np.random.default_rng(11)
+    inputs = [float_bits(n, 7) if key_type == "float32" else DataGenerator(12).generate(n)[0]]
+    low = rng.choice(1 << 16, size=40, replace=False).astype(np.uint32)          # long runs below the third digit
+    inputs.append((low[rng.integers(0, 40, n)] | (rng.integers(0, 1 << 16, n, dtype=np.uint32) << np.uint32(16))).astype(np.uint32))
+    for bits in inputs:
+        ek, _ = oracle.sort_ex(bits, np.arange(n, dtype=np.uint32), key_type=kt, descending=descending)
+        gk, _ = run_ex(s, bits, key_type=kt, descending=descending)
+        assert np.array_equal(gk, ek)
+    s.close()
+
+
 def test_typed_tensors_sort_like_torch(sorter):
     g = torch.Generator(device="cpu").manual_seed(5)
     f = torch.randn(500_000, generator=g).to(DEV)
