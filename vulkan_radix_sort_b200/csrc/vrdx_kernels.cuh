@@ -7,13 +7,16 @@
 // with a different decomposition:
 //   ResetKernel + HistogramKernel[Private]   onesweep: ONE read of the keys builds all four 256-bin digit
 //                     histograms; the last CTA to finish exclusive-scans them in place (no spine launch).
-//   UpsweepKernel + SpineReduce/ApplyKernel  reduce-then-scan: per-tile digit prefixes (16-bit, inside a chunk
-//                     of 8 tiles), chunk prefixes and the global digit offsets of one pass.
+//   UpsweepKernel + SpineKernel  reduce-then-scan: per-tile digit prefixes (16-bit, inside a chunk of 8 tiles),
+//                     chunk prefixes and the global digit offsets of one pass; keys-only sorts over all 32 bits
+//                     also get one flag byte per tile (its keys are one / two runs below the digit).
 //   PassKernel        one launch per pass, one tile per CTA: warp-level multi-split ranking (returning
 //                     shared-memory atomicAdd on warp-private counters, collisions repaired exactly with a
 //                     REDUX.OR bloom filter + MATCH.ANY on the few colliding lanes), tile-local reorder
 //                     through shared memory, run-wise coalesced scatter; the tile's global offsets come
 //                     from a single-pass decoupled look-back (MODE 0) or from the upsweep tables (MODE 1).
+//                     Flagged tiles of a keys-only reduce-then-scan pass skip the warp-private ranking
+//                     (TileBlockFree: one returning atomic per key on a block-wide cursor row).
 //                     Keys and values are two separate arrays end to end, as in the reference.
 // Stability: a warp owns 32*IPT consecutive keys and ranks them item by item, lane by lane, so
 // (warp, item, lane) order == index order — the same argument as downsweep.slang:79-80.
@@ -1114,18 +1117,17 @@ PassKernel(const PassArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Reduce-then-scan variant (the reference's upsweep / spine / downsweep decomposition,
-// src/shader/upsweep.slang, spine.slang, downsweep.slang), kept for A/B measurement against the
-// single-pass look-back and as the path for N >= 2^30 (full 32-bit counts, no flag bits).  On
-// B200 it is the faster composition from N ~ 2^25 up (profiles/r01_sweep_n.txt): the scatter pass
-// has no inter-CTA dependency at all.  Per pass, four launches:
-//   UpsweepKernel    4 B/key read; one CTA counts a CHUNK of kSpineChunk consecutive tiles and
-//                    writes tile_hist[tile][256] plus the chunk's column sums chunk_sums[chunk][256]
-//   SpineReduceKernel + SpineApplyKernel  exclusive scan of chunk_sums over chunks (coalesced,
-//                    segment-parallel) + global digit offsets (last CTA done)
-//   OnesweepKernel<Cfg, 1>  4 B/key read + 4 B/key write; a tile's offset for digit d is
-//                    chunk_sums[chunk][d] + the tile_hist rows of the <= kSpineChunk-1 earlier
-//                    tiles of its chunk, fetched while the tile is being reordered
+// Reduce-then-scan (the reference's upsweep / spine / downsweep decomposition, src/shader/upsweep.slang,
+// spine.slang, downsweep.slang): what AUTO runs from 2^25 keys / 2^27 pairs up
+// (profiles/r02/s_sweep_n_auto_thresholds.txt) and the only path for N >= 2^30 (full 32-bit counts, no flag
+// bits).  The scatter pass has no inter-CTA dependency at all.  Per pass, three launches:
+//   UpsweepKernel    4 B/key read (128-bit loads); one CTA counts a CHUNK of kSpineChunk consecutive tiles and
+//                    writes the 16-bit inclusive prefixes tile_hist[tile][256], the chunk's column sums
+//                    chunk_sums[chunk][256] and (keys-only) one flag byte per tile
+//   SpineKernel      exclusive scan of chunk_sums over chunks (128 co-resident segments exchange their
+//                    sums once) + global digit offsets and the identity flag (last segment)
+//   PassKernel<Cfg, 1>  4 B/key read + 4 B/key write; a tile's offset for digit d is
+//                    chunk_sums[chunk][d] + the tile_hist row of the tile before it in its chunk
 // Algorithmic overhead vs onesweep: the keys are read twice per pass (12 instead of 8 B/key).
 // ------------------------------------------------------------------------------------------
 constexpr int kUpsweepThreads = 256;
@@ -1258,8 +1260,9 @@ UpsweepKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t
 }
 
 // Spine: exclusive scan of chunk_sums[chunk][256] over chunks for every digit, and the global
-// digit offsets of this pass (spine.slang:32-60 and :62-83).  Two coalesced kernels (thread =
-// digit, so every row access is one 1 KB line):
+// digit offsets of this pass (spine.slang:32-60 and :62-83).  Thread = digit, so every row access is one
+// 1 KB line.  SpineKernel (below, what ships) does it in one launch; the two-kernel form it replaced is kept
+// behind VRDX_SPINE_FUSED=0 for A/B:
 //   SpineReduceKernel  CTA s sums the rows of segment s -> seg[s][256]; the LAST CTA to finish
 //                      scans seg over segments in place and turns the per-digit totals into the
 //                      global digit offsets hdr->global_hist[pass]
