@@ -436,6 +436,23 @@ def test_full_size_uniform_keys_and_pairs(sorter, oracle, log2n):
     _property_check(oracle, k, to_np(dk), to_np(dv))
 
 
+@pytest.mark.parametrize("n", [(1 << 25) - 1, 1 << 25, (1 << 26) + 4099, (1 << 27) - 1, 1 << 27])
+def test_counts_on_both_sides_of_the_auto_crossovers(sorter, oracle, n):
+    """AUTO switches from onesweep to reduce-then-scan at 2^25 keys / 2^27 pairs; the storage is laid out for the
+    composition that runs (csrc/vrdx_api.cu SorterLayout).  Property check on both sides of both thresholds."""
+    k = DataGenerator(n % 97).generate(n)[0]
+    dk = to_dev(k)
+    sorter.sort(dk)
+    torch.cuda.synchronize()
+    _property_check(oracle, k, to_np(dk))
+    del dk
+    dk = to_dev(k)
+    dv = torch.arange(n, dtype=torch.int32, device=DEV)
+    sorter.sort_key_value(dk, dv)
+    torch.cuda.synchronize()
+    _property_check(oracle, k, to_np(dk), to_np(dv))
+
+
 @pytest.mark.parametrize("seed", [1, 2, 3])
 @pytest.mark.parametrize("dist", ["skewed", "bits8", "bits4", "all_zero", "all_ones", "sorted", "reverse", "sentinel_mix"])
 def test_indirect_adversarial_non_power_of_two(sorter, oracle, dist, seed):
