@@ -82,8 +82,8 @@ inline StorageLayout ComputeLayout(uint64_t max_count, uint32_t min_tile, uint64
   const uint64_t one_bytes = one_count ? (CeilDiv(one_count, min_tile) + 1) * row : 0;
   const uint64_t rts_a = wide_rows ? tiles * row : tiles * (row / 2);
   // (+ one byte per tile after the segment sums: the upsweep's "all keys agree below the digit" tile flags)
-  const uint64_t rts_b =
-      wide_rows ? tiles * row : (CeilDiv(tiles, kSpineChunkTiles) + kSpineSegmentRows + 1 + CeilDiv(tiles, row)) * row;
+  const uint64_t spine_rows = kSpineSegmentRows + 1 + CeilDiv(tiles, row);  // segment sums + the flag bytes
+  const uint64_t rts_b = ((wide_rows ? tiles : CeilDiv(tiles, kSpineChunkTiles)) + spine_rows) * row;
   // Tables and scratch halves start on kTableAlignment (256 B) boundaries of the storage: a warp's 128-byte row of
   // the scratch keys / values is then one L1 line when the caller's storage is itself 256-byte aligned.
   l.header_offset = 0;
