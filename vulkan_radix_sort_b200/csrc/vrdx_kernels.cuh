@@ -839,19 +839,26 @@ __device__ __forceinline__ void TileCopy(const PassArgs& a, uint64_t tile_start,
   constexpr bool KV = Cfg::kKeyValue;
   const uint32_t* kin = a.keys_in + tile_start;
   uint32_t* kout = a.keys_out + tile_start;
-  uint32_t ck[IPT], cv[KV ? IPT : 1];
+  // (pairs go in two halves: 2 x IPT words in flight per thread would not fit the register budget of the pass kernel
+  // this is inlined into, and spilled)
+  constexpr int kStep = KV ? (IPT + 1) / 2 : IPT;
 #pragma unroll
-  for (int i = 0; i < IPT; ++i) {  // all loads first: the stores below may alias them as far as the compiler knows
-    const uint32_t idx = i * THREADS + tid;
-    ck[i] = idx < tile_count ? KeyOut(KeyIn(LdStream(kin + idx), dg.cin), dg.cout) : 0u;
-    if (KV) cv[i] = idx < tile_count ? LdStream(a.vals_in + tile_start + idx) : 0u;
-  }
+  for (int i0 = 0; i0 < IPT; i0 += kStep) {
+    uint32_t ck[kStep], cv[KV ? kStep : 1];
 #pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const uint32_t idx = i * THREADS + tid;
-    if (idx < tile_count) {
-      kout[idx] = ck[i];
-      if (KV) a.vals_out[tile_start + idx] = cv[i];
+    for (int j = 0; j < kStep; ++j) {  // all loads first: the stores below may alias them as far as the compiler knows
+      const uint32_t idx = (i0 + j) * THREADS + tid;
+      const bool in = i0 + j < IPT && idx < tile_count;
+      ck[j] = in ? KeyOut(KeyIn(LdStream(kin + idx), dg.cin), dg.cout) : 0u;
+      if (KV) cv[j] = in ? LdStream(a.vals_in + tile_start + idx) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < kStep; ++j) {
+      const uint32_t idx = (i0 + j) * THREADS + tid;
+      if (i0 + j < IPT && idx < tile_count) {
+        kout[idx] = ck[j];
+        if (KV) a.vals_out[tile_start + idx] = cv[j];
+      }
     }
   }
 }
@@ -1279,6 +1286,7 @@ __device__ __forceinline__ void SpineGeometry(uint32_t n, uint32_t tile_size, ui
   rows_per = (chunks + gridDim.x - 1) / gridDim.x;
 }
 
+#if !VRDX_SPINE_FUSED
 __global__ void __launch_bounds__(kRadix)
 SpineReduceKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint32_t tile_size, uint32_t fixed_rows,
                   uint32_t pass, const uint32_t* __restrict__ chunk_sums, uint32_t* __restrict__ seg,
@@ -1352,6 +1360,7 @@ SpineApplyKernel(const uint32_t* __restrict__ indirect, uint32_t n_or_max, uint3
   }
   StampEnd(ts_end);
 }
+#endif  // !VRDX_SPINE_FUSED
 
 // SpineKernel — the two kernels above as one (what ships; VRDX_SPINE_FUSED=0 keeps the pair for A/B).  The grid is
 // at most kSpineSegments (128) small CTAs, all co-resident on a 148-SM part, so a CTA may wait for the others:
