@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--experiment", type=int, default=0)
     ap.add_argument("--dist", default="uniform")
+    ap.add_argument("--pairs-only-shape", action="store_true")
     ap.add_argument("--kinds", nargs="+", default=["keys", "kv"])
     args = ap.parse_args()
     tag = os.path.basename(os.environ.get("VRDX_LIB", "product"))
@@ -37,7 +38,8 @@ def main():
     for shape in args.shapes:
         for algo in args.algos:
             try:
-                s = Sorter(0, algorithm=algo, reserved=(shape + 1, shape + 1, args.experiment))
+                # (--pairs-only-shape: the index selects a key-value shape, the keys shape stays the default)
+                s = Sorter(0, algorithm=algo, reserved=(0 if args.pairs_only_shape else shape + 1, shape + 1, args.experiment))
             except RuntimeError as e:
                 print(f"[{tag}] shape {shape} algo {algo}: {e}")
                 continue
